@@ -1,0 +1,641 @@
+// mpe_kernels.cu -- the hot path of multiagent-particle-envs for a batch of worlds, sm_100a.
+//
+//   kFusedStep  MultiAgentEnv.step            environment.py:80-104   (one launch)
+//   kSetAction  MultiAgentEnv._set_action     environment.py:144-192
+//   kWorldStep  World.step                    core.py:117-131
+//   kObserve    scenario.observation/reward + step glue (also used by reset)
+//
+// All four are the same kernel template with phases compiled in or out, so the fused step is
+// bit-identical to set_action -> world_step -> observe.
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <utility>
+
+#include "mpe_scenarios.cuh"
+
+namespace mpe {
+
+template <int... I, class F>
+__device__ __forceinline__ void static_for_impl(std::integer_sequence<int, I...>, F &&f) {
+    (f(std::integral_constant<int, I>{}), ...);
+}
+template <int N, class F>
+__device__ __forceinline__ void static_for(F &&f) {
+    static_for_impl(std::make_integer_sequence<int, N>{}, static_cast<F &&>(f));
+}
+
+template <class P>
+struct Shape {
+    __host__ __device__ static constexpr int sum_act() { int s = 0; for (int i = 0; i < P::A; ++i) s += 32 * (P::act_dim(i) | 1); return s; }
+    __host__ __device__ static constexpr int max_obs() { int m = 0; for (int i = 0; i < P::A; ++i) { int v = 32 * (P::obs_dim(i) | 1); m = v > m ? v : m; } return m; }
+    __host__ __device__ static constexpr int act_off(int i) { int s = 0; for (int j = 0; j < i; ++j) s += 32 * (P::act_dim(j) | 1); return s; }
+    // floats of warp-private staging: action tiles of all agents, then one observation tile
+    static constexpr int kActFloats = (sum_act() + 3) & ~3;
+    static constexpr int kWarpFloats = kActFloats + ((max_obs() + 3) & ~3);
+    static constexpr int kSmemBytes = kWarpsPerBlock * kWarpFloats * 4;
+    static constexpr int kNC = P::NS * P::DIMC;
+};
+
+// World.step physics for one world held in registers (core.py:134-169)
+template <class P>
+__device__ __forceinline__ void physics(const DevDesc &d, typename P::W &w, const float (&ux)[P::A],
+                                        const float (&uy)[P::A]) {
+    constexpr int A = P::A, L = P::L;
+    float fx[A], fy[A];
+#pragma unroll
+    for (int i = 0; i < A; ++i) {  // apply_action_force (core.py:134-140)
+        fx[i] = ux[i];
+        fy[i] = uy[i];
+    }
+    const float k = d.contact_margin, cf = d.contact_force;
+    // apply_environment_force (core.py:143-155): pairs (a, b), a < b, agents then landmarks.
+    // Landmark-landmark pairs move nothing and are dropped at compile time.
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+#pragma unroll
+        for (int b = a + 1; b < A + L; ++b) {
+            const bool b_agent = b < A;
+            const int bi = b_agent ? b : 0, bl = b_agent ? 0 : b - A;
+            const bool collide = ((d.a_collide >> a) & 1u) &&
+                                 (b_agent ? ((d.a_collide >> bi) & 1u) : ((d.l_collide >> bl) & 1u));
+            if (!collide) continue;  // get_collision_force (core.py:181-182); warp-uniform
+            const float bx = b_agent ? w.px[bi] : w.lx[bl];
+            const float by = b_agent ? w.py[bi] : w.ly[bl];
+            const float sb = b_agent ? d.a_size[bi] : d.l_size[bl];
+            const float dx = w.px[a] - bx, dy = w.py[a] - by;              // :186
+            const float dist = sqrtf(dx * dx + dy * dy);                    // :187
+            const float dist_min = d.a_size[a] + sb;                        // :189
+            const float pen = softplus(-(dist - dist_min) / k) * k;         // :191-192
+            const float f_x = cf * dx / dist * pen;                         // :193
+            const float f_y = cf * dy / dist * pen;
+            if ((d.a_movable >> a) & 1u) {                                  // :194, 149-151
+                fx[a] = f_x + fx[a];
+                fy[a] = f_y + fy[a];
+            }
+            if (b_agent && ((d.a_movable >> bi) & 1u)) {                    // :195, 152-154
+                fx[bi] = -f_x + fx[bi];
+                fy[bi] = -f_y + fy[bi];
+            }
+        }
+    }
+    // integrate_state (core.py:158-169)
+#pragma unroll
+    for (int i = 0; i < A; ++i) {
+        if (!((d.a_movable >> i) & 1u)) continue;
+        float vx = w.vx[i] * d.keep, vy = w.vy[i] * d.keep;                 // :161
+        vx += (fx[i] / d.a_mass[i]) * d.dt;                                 // :163
+        vy += (fy[i] / d.a_mass[i]) * d.dt;
+        const float ms = d.a_max_speed[i];
+        if (ms >= 0.0f) {                                                   // :164-168
+            const float speed = sqrtf(vx * vx + vy * vy);
+            if (speed > ms) {
+                vx = vx / speed * ms;
+                vy = vy / speed * ms;
+            }
+        }
+        w.px[i] += vx * d.dt;                                               // :169
+        w.py[i] += vy * d.dt;
+        w.vx[i] = vx;
+        w.vy[i] = vy;
+    }
+}
+
+template <class P, int MODE>
+__global__ void __launch_bounds__(kThreads) mpe_kernel(const __grid_constant__ StepArgs a) {
+    constexpr int A = P::A, L = P::L, NC = Shape<P>::kNC;
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t n = a.n;
+    const int64_t w0 = (static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + warp) * 32;
+    if (w0 >= n) return;  // whole warp exits together
+    const int rows = (n - w0) < 32 ? static_cast<int>(n - w0) : 32;
+    const bool active = lane < rows;
+    const int64_t wi = w0 + (active ? lane : 0);  // inactive lanes shadow row 0 and never store
+    float *s_act = smem + warp * Shape<P>::kWarpFloats;
+    float *s_obs = s_act + Shape<P>::kActFloats;
+    const DevDesc &d = a.d;
+
+    typename P::W w;
+    // ---- state loads (issued first so they overlap the action staging) ---------------------
+    if constexpr (MODE != kSetAction) {
+#pragma unroll
+        for (int i = 0; i < A; ++i) {
+            const float4 v = a.pv[i * n + wi];
+            w.px[i] = v.x; w.py[i] = v.y; w.vx[i] = v.z; w.vy[i] = v.w;
+        }
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+            const float2 v = a.lm[l * n + wi];
+            w.lx[l] = v.x; w.ly[l] = v.y;
+        }
+        if constexpr (MODE == kObserve && NC > 0) {
+#pragma unroll
+            for (int q = 0; q < NC; ++q) w.c[q] = a.comm[q * n + wi];
+        }
+    }
+
+    float ux[A], uy[A];
+    float cact[NC > 0 ? NC : 1];
+    // ---- MultiAgentEnv._set_action (environment.py:144-192) --------------------------------
+    if constexpr (MODE == kFusedStep || MODE == kSetAction) {
+        static_for<A>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            constexpr int AD = P::act_dim(i);
+            constexpr int OFF = Shape<P>::act_off(i);
+            tile_load<AD>(s_act + OFF, a.act[i] + w0 * AD, rows, lane);
+        });
+        __syncwarp();
+        static_for<A>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            constexpr int AD = P::act_dim(i);
+            constexpr int OFF = Shape<P>::act_off(i);
+            const float *row = s_act + OFF + lane * Tile<AD>::kStride;
+            int off = 0;
+            float x = 0.0f, y = 0.0f;                                       // :145
+            if constexpr (P::movable(i)) {
+                float p0 = row[0], p1 = row[1], p2 = row[2], p3 = row[3], p4 = row[4];
+                if (a.flags & MPE_FLAG_FORCE_DISCRETE_ACTION) {             // :169-172 (first arg-max)
+                    int best = 0;
+                    float bv = p0;
+                    if (p1 > bv) { bv = p1; best = 1; }
+                    if (p2 > bv) { bv = p2; best = 2; }
+                    if (p3 > bv) { bv = p3; best = 3; }
+                    if (p4 > bv) { bv = p4; best = 4; }
+                    p1 = best == 1 ? 1.0f : 0.0f; p2 = best == 2 ? 1.0f : 0.0f;
+                    p3 = best == 3 ? 1.0f : 0.0f; p4 = best == 4 ? 1.0f : 0.0f;
+                }
+                x += p1 - p2;                                               // :174
+                y += p3 - p4;                                               // :175
+                x *= d.a_sens[i];                                           // :178-181
+                y *= d.a_sens[i];
+                off = 5;
+            }
+            ux[i] = x;
+            uy[i] = y;
+            if constexpr (i < P::NS) {                                      // :183-190 speakers come first
+#pragma unroll
+                for (int q = 0; q < P::DIMC; ++q) cact[i * P::DIMC + q] = row[off + q];
+            }
+        });
+        if constexpr (MODE == kSetAction) {
+            if (active) {
+#pragma unroll
+                for (int i = 0; i < A; ++i) a.u[i * n + wi] = make_float2(ux[i], uy[i]);
+#pragma unroll
+                for (int q = 0; q < NC; ++q) a.c[q * n + wi] = cact[q];
+            }
+            return;
+        }
+    }
+    if constexpr (MODE == kWorldStep) {
+#pragma unroll
+        for (int i = 0; i < A; ++i) {
+            const float2 v = a.u[i * n + wi];
+            ux[i] = v.x; uy[i] = v.y;
+        }
+#pragma unroll
+        for (int q = 0; q < NC; ++q) cact[q] = a.c[q * n + wi];
+    }
+
+    // ---- World.step (core.py:117-131) --------------------------------------------------------
+    if constexpr (MODE == kFusedStep || MODE == kWorldStep) {
+        physics<P>(d, w, ux, uy);
+#pragma unroll
+        for (int q = 0; q < NC; ++q) w.c[q] = cact[q];  // update_agent_state (core.py:171-177)
+        if (active) {
+#pragma unroll
+            for (int i = 0; i < A; ++i)
+                if ((d.a_movable >> i) & 1u) a.pv[i * n + wi] = make_float4(w.px[i], w.py[i], w.vx[i], w.vy[i]);
+#pragma unroll
+            for (int q = 0; q < NC; ++q) a.comm[q * n + wi] = w.c[q];
+        }
+        if constexpr (MODE == kWorldStep) return;
+    }
+
+    // ---- observation / reward / done / info (environment.py:92-102) -------------------------
+    float rew[A];
+    float info[(P::INFO > 0 ? P::INFO : 1) * A];
+    P::reward(d, w, rew, (P::INFO > 0 && a.info != nullptr) ? info : nullptr);
+    if (a.flags & MPE_FLAG_SHARED_REWARD) {                                  // :100-102 np.sum(reward_n)
+        float s = 0.0f;
+#pragma unroll
+        for (int i = 0; i < A; ++i) s += rew[i];
+#pragma unroll
+        for (int i = 0; i < A; ++i) rew[i] = s;
+    }
+    static_for<A>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        constexpr int OD = P::obs_dim(i);
+        RowWriter o{s_obs + lane * Tile<OD>::kStride};
+        P::template observe<i>(d, w, o);
+        __syncwarp();
+        tile_store<OD>(a.obs[i] + w0 * OD, s_obs, rows, lane);
+        __syncwarp();
+    });
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < A; ++i) {
+            a.rew[i * n + wi] = rew[i];
+            a.done[i * n + wi] = 0;  // done_callback is None (make_env.py:41-43, environment.py:132-135)
+        }
+        if (P::INFO > 0 && a.info != nullptr) {
+#pragma unroll
+            for (int q = 0; q < P::INFO * A; ++q) a.info[q * n + wi] = info[q];
+        }
+    }
+}
+
+// ---- reset: i.i.d. uniform positions (e.g. simple_spread.py:38-45) -----------------------------
+struct ResetArgs {
+    int64_t n;
+    int A, L, NC, G;
+    float4 *pv;
+    float2 *lm;
+    float *comm;
+    int32_t *goal;
+    const uint8_t *mask;
+    uint64_t seed, world_offset, epoch;
+    float agent_range, landmark_range[kMaxL];
+    int goal_mod[4];
+};
+
+__global__ void __launch_bounds__(256) reset_kernel(const __grid_constant__ ResetArgs a) {
+    const int64_t w = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (w >= a.n) return;
+    if (a.mask != nullptr && a.mask[w] == 0) return;
+    const uint64_t gw = a.world_offset + static_cast<uint64_t>(w);
+    const uint2 key = make_uint2(static_cast<uint32_t>(a.seed), static_cast<uint32_t>(a.seed >> 32));
+    // one Philox block = 4 x 32 bits = two entities' (x, y); counter = (world lo, world hi, epoch, block)
+    const int E = a.A + a.L;
+    for (int e = 0; e < E; e += 2) {
+        const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(gw), static_cast<uint32_t>(gw >> 32),
+                                                 static_cast<uint32_t>(a.epoch), static_cast<uint32_t>(e >> 1)), key);
+        const uint32_t bits[4] = {r.x, r.y, r.z, r.w};
+        for (int k = 0; k < 2 && e + k < E; ++k) {
+            const int ent = e + k;
+            if (ent < a.A) {
+                const float x = uniform_from_bits(bits[2 * k], -a.agent_range, a.agent_range);
+                const float y = uniform_from_bits(bits[2 * k + 1], -a.agent_range, a.agent_range);
+                a.pv[ent * a.n + w] = make_float4(x, y, 0.0f, 0.0f);
+            } else {
+                const float rg = a.landmark_range[ent - a.A];
+                a.lm[(ent - a.A) * a.n + w] = make_float2(uniform_from_bits(bits[2 * k], -rg, rg),
+                                                           uniform_from_bits(bits[2 * k + 1], -rg, rg));
+            }
+        }
+    }
+    for (int q = 0; q < a.NC; ++q) a.comm[q * a.n + w] = 0.0f;
+    if (a.G > 0) {
+        const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(gw), static_cast<uint32_t>(gw >> 32),
+                                                 static_cast<uint32_t>(a.epoch), 0x80000000u), key);
+        const uint32_t bits[4] = {r.x, r.y, r.z, r.w};
+        for (int g = 0; g < a.G && g < 4; ++g) a.goal[g * a.n + w] = static_cast<int32_t>(bits[g] % static_cast<uint32_t>(a.goal_mod[g]));
+    }
+}
+
+// ---- program table -----------------------------------------------------------------------------
+typedef void (*KernelFn)(StepArgs);
+
+struct Program {
+    int scenario;
+    bool (*validate)(const mpe_desc &);
+    KernelFn fn[4];
+    int smem_bytes;
+    int A, L, NS, DIMC, INFO, G;
+    int obs_dim[kMaxA], act_dim[kMaxA];
+};
+
+template <class P>
+static Program make_program() {
+    Program p{};
+    p.scenario = P::kScenario;
+    p.validate = &P::validate;
+    p.fn[kFusedStep] = mpe_kernel<P, kFusedStep>;
+    p.fn[kSetAction] = mpe_kernel<P, kSetAction>;
+    p.fn[kWorldStep] = mpe_kernel<P, kWorldStep>;
+    p.fn[kObserve] = mpe_kernel<P, kObserve>;
+    p.smem_bytes = Shape<P>::kSmemBytes;
+    p.A = P::A; p.L = P::L; p.NS = P::NS; p.DIMC = P::DIMC; p.INFO = P::INFO; p.G = P::G;
+    for (int i = 0; i < P::A; ++i) { p.obs_dim[i] = P::obs_dim(i); p.act_dim[i] = P::act_dim(i); }
+    return p;
+}
+
+static const Program *programs(int *count) {
+    static const Program table[] = {
+        make_program<Simple<1, 1>>(),
+        make_program<Spread<2>>(), make_program<Spread<3>>(), make_program<Spread<4>>(),
+        make_program<Spread<5>>(), make_program<Spread<6>>(),
+        make_program<Tag<3, 1, 2>>(),
+        make_program<WorldComm<4, 2, 1, 2>>(),
+    };
+    *count = static_cast<int>(sizeof(table) / sizeof(table[0]));
+    return table;
+}
+
+}  // namespace mpe
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+using namespace mpe;
+
+static_assert(sizeof(mpe_desc) == 480, "mpe_desc layout is part of the ABI (mirrored by _lib.MpeDesc)");
+
+struct mpe_env {
+    mpe_desc desc;
+    DevDesc dev;
+    const Program *prog;
+    int64_t n;
+    int device;
+};
+
+static thread_local char g_cuda_err[256] = "";
+static long long g_launches = 0;
+
+static int cuda_fail(cudaError_t e, const char *what) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", what, cudaGetErrorString(e));
+    return MPE_ERR_CUDA;
+}
+#define CUDA_TRY(expr)                                     \
+    do {                                                   \
+        cudaError_t e_ = (expr);                           \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #expr); \
+    } while (0)
+
+static uint32_t mask_of(const uint8_t *v, int n) {
+    uint32_t m = 0;
+    for (int i = 0; i < n; ++i) if (v[i]) m |= 1u << i;
+    return m;
+}
+
+extern "C" int mpe_create(const mpe_desc *desc, int64_t n_env, int device, mpe_handle *out) {
+    if (!desc || !out || n_env <= 0) return MPE_ERR_BAD_ARG;
+    if (desc->abi_version != MPE_ABI_VERSION) return MPE_ERR_BAD_DESC;
+    if (desc->n_agents < 1 || desc->n_agents > MPE_MAX_AGENTS || desc->n_landmarks < 0 ||
+        desc->n_landmarks > MPE_MAX_LANDMARKS)
+        return MPE_ERR_BAD_DESC;
+    int count = 0;
+    const Program *tab = programs(&count);
+    const Program *prog = nullptr;
+    bool scenario_known = false;
+    for (int i = 0; i < count; ++i) {
+        if (tab[i].scenario != desc->scenario) continue;
+        scenario_known = true;
+        if (tab[i].validate(*desc)) { prog = &tab[i]; break; }
+    }
+    if (!prog) return scenario_known ? MPE_ERR_BAD_DESC : MPE_ERR_UNSUPPORTED;
+    if (device != -1) {  // device == -1: shape-only handle (no CUDA call is made; launches are refused)
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return MPE_ERR_NO_DEVICE;
+        int major = 0;
+        CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+        if (major != 10) return MPE_ERR_NO_DEVICE;  // sm_100a cubin only
+        int prev = 0;
+        CUDA_TRY(cudaGetDevice(&prev));
+        CUDA_TRY(cudaSetDevice(device));
+        for (int m = 0; m < 4; ++m)
+            CUDA_TRY(cudaFuncSetAttribute(prog->fn[m], cudaFuncAttributeMaxDynamicSharedMemorySize, prog->smem_bytes));
+        CUDA_TRY(cudaSetDevice(prev));
+    }
+
+    mpe_env *h = new (std::nothrow) mpe_env();
+    if (!h) return MPE_ERR_BAD_ARG;
+    h->desc = *desc;
+    h->prog = prog;
+    h->n = n_env;
+    h->device = device;
+    DevDesc &d = h->dev;
+    memset(&d, 0, sizeof(d));
+    d.dt = static_cast<float>(desc->dt);
+    d.keep = static_cast<float>(1.0 - desc->damping);
+    d.contact_force = static_cast<float>(desc->contact_force);
+    d.contact_margin = static_cast<float>(desc->contact_margin);
+    for (int i = 0; i < desc->n_agents; ++i) {
+        d.a_size[i] = static_cast<float>(desc->agent_size[i]);
+        d.a_mass[i] = static_cast<float>(desc->agent_mass[i]);
+        d.a_sens[i] = static_cast<float>(desc->agent_sens[i]);
+        d.a_max_speed[i] = desc->agent_max_speed[i] < 0 ? -1.0f : static_cast<float>(desc->agent_max_speed[i]);
+    }
+    for (int l = 0; l < desc->n_landmarks; ++l) d.l_size[l] = static_cast<float>(desc->landmark_size[l]);
+    d.a_movable = mask_of(desc->agent_movable, desc->n_agents);
+    d.a_collide = mask_of(desc->agent_collide, desc->n_agents);
+    d.a_silent = mask_of(desc->agent_silent, desc->n_agents);
+    d.a_adversary = mask_of(desc->agent_adversary, desc->n_agents);
+    d.l_collide = mask_of(desc->landmark_collide, desc->n_landmarks);
+    *out = h;
+    return MPE_OK;
+}
+
+extern "C" int mpe_destroy(mpe_handle h) {
+    if (!h) return MPE_ERR_BAD_ARG;
+    delete h;
+    return MPE_OK;
+}
+
+extern "C" int mpe_num_agents(mpe_handle h) { return h ? h->prog->A : MPE_ERR_BAD_ARG; }
+extern "C" int64_t mpe_num_envs(mpe_handle h) { return h ? h->n : MPE_ERR_BAD_ARG; }
+extern "C" int mpe_obs_dim(mpe_handle h, int i) { return (h && i >= 0 && i < h->prog->A) ? h->prog->obs_dim[i] : MPE_ERR_BAD_ARG; }
+extern "C" int mpe_act_dim(mpe_handle h, int i) { return (h && i >= 0 && i < h->prog->A) ? h->prog->act_dim[i] : MPE_ERR_BAD_ARG; }
+extern "C" int mpe_num_speakers(mpe_handle h) { return h ? h->prog->NS : MPE_ERR_BAD_ARG; }
+extern "C" int mpe_num_goals(mpe_handle h) { return h ? h->prog->G : MPE_ERR_BAD_ARG; }
+extern "C" int mpe_info_dim(mpe_handle h) { return h ? h->prog->INFO : MPE_ERR_BAD_ARG; }
+
+extern "C" int64_t mpe_bytes_per_env_step(mpe_handle h) {
+    if (!h) return MPE_ERR_BAD_ARG;
+    // read agent pos+vel, landmark pos, actions; write agent pos+vel, obs,
+    // rewards (+ speaker comm state), 1 done byte per agent
+    const Program *p = h->prog;
+    int64_t f = 4 * p->A + 2 * p->L + 4 * p->A + p->A + p->NS * p->DIMC;
+    for (int i = 0; i < p->A; ++i) f += p->act_dim[i] + p->obs_dim[i];
+    return 4 * f + p->A;
+}
+
+static int launch(mpe_handle h, int mode, StepArgs &args, void *stream) {
+    if (h->device < 0) return MPE_ERR_NO_DEVICE;
+    args.d = h->dev;
+    args.n = h->n;
+    const int64_t warps = (h->n + 31) / 32;
+    const int64_t blocks = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    if (blocks > 0x7fffffffLL) return MPE_ERR_BAD_ARG;
+    int prev = 0;
+    CUDA_TRY(cudaGetDevice(&prev));
+    if (prev != h->device) CUDA_TRY(cudaSetDevice(h->device));
+    void *params[] = {&args};
+    cudaError_t e = cudaLaunchKernel(reinterpret_cast<const void *>(h->prog->fn[mode]), dim3(static_cast<unsigned>(blocks)),
+                                     dim3(kThreads), params, h->prog->smem_bytes, static_cast<cudaStream_t>(stream));
+    if (prev != h->device) cudaSetDevice(prev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernel");
+    __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED);
+    return MPE_OK;
+}
+
+static bool ok16(const void *p) { return p != nullptr && (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static bool ok8(const void *p) { return p != nullptr && (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
+static bool ok4(const void *p) { return p != nullptr && (reinterpret_cast<uintptr_t>(p) & 3u) == 0; }
+
+static int fill_state(mpe_handle h, StepArgs &a, void *pv, const void *lm, float *comm, const int32_t *goal,
+                      bool need_goal = true) {
+    const Program *p = h->prog;
+    if (!ok16(pv)) return MPE_ERR_BAD_ARG;
+    if (p->L > 0 && !ok8(lm)) return MPE_ERR_BAD_ARG;
+    if (p->NS * p->DIMC > 0 && !ok4(comm)) return MPE_ERR_BAD_ARG;
+    if (need_goal && p->G > 0 && !ok4(goal)) return MPE_ERR_BAD_ARG;
+    a.pv = static_cast<float4 *>(pv);
+    a.lm = static_cast<const float2 *>(lm);
+    a.comm = comm;
+    a.goal = goal;
+    return MPE_OK;
+}
+
+static int fill_outputs(mpe_handle h, StepArgs &a, float *const *obs_n, float *rew, uint8_t *done, float *info) {
+    const Program *p = h->prog;
+    if (!obs_n || !ok4(rew) || !done) return MPE_ERR_BAD_ARG;
+    for (int i = 0; i < p->A; ++i) {
+        if (!ok4(obs_n[i])) return MPE_ERR_BAD_ARG;
+        a.obs[i] = obs_n[i];
+    }
+    a.rew = rew;
+    a.done = done;
+    a.info = p->INFO > 0 ? info : nullptr;
+    return MPE_OK;
+}
+
+static int fill_actions(mpe_handle h, StepArgs &a, const float *const *act_n) {
+    if (!act_n) return MPE_ERR_BAD_ARG;
+    for (int i = 0; i < h->prog->A; ++i) {
+        if (!ok4(act_n[i])) return MPE_ERR_BAD_ARG;
+        a.act[i] = act_n[i];
+    }
+    return MPE_OK;
+}
+
+extern "C" int mpe_set_action(mpe_handle h, const float *const *act_n, float *u, float *c, uint32_t flags, void *stream) {
+    if (!h || !ok8(u)) return MPE_ERR_BAD_ARG;
+    if (flags & MPE_FLAG_DISCRETE_ACTION_INPUT) return MPE_ERR_UNSUPPORTED;
+    if (h->prog->NS * h->prog->DIMC > 0 && !ok4(c)) return MPE_ERR_BAD_ARG;
+    StepArgs a{};
+    int r = fill_actions(h, a, act_n);
+    if (r) return r;
+    a.u = reinterpret_cast<float2 *>(u);
+    a.c = c;
+    a.flags = flags;
+    return launch(h, kSetAction, a, stream);
+}
+
+extern "C" int mpe_world_step(mpe_handle h, void *pv, const void *lm, float *comm, const float *u, const float *c, void *stream) {
+    if (!h || !ok8(u)) return MPE_ERR_BAD_ARG;
+    if (h->prog->NS * h->prog->DIMC > 0 && !ok4(c)) return MPE_ERR_BAD_ARG;
+    StepArgs a{};
+    int r = fill_state(h, a, pv, lm, comm, nullptr, false);
+    if (r) return r;
+    a.u = reinterpret_cast<float2 *>(const_cast<float *>(u));
+    a.c = const_cast<float *>(c);
+    return launch(h, kWorldStep, a, stream);
+}
+
+extern "C" int mpe_observe(mpe_handle h, const void *pv, const void *lm, const float *comm, const int32_t *goal,
+                           float *const *obs_n, float *rew, uint8_t *done, float *info, uint32_t flags, void *stream) {
+    if (!h) return MPE_ERR_BAD_ARG;
+    StepArgs a{};
+    int r = fill_state(h, a, const_cast<void *>(pv), lm, const_cast<float *>(comm), goal);
+    if (r) return r;
+    r = fill_outputs(h, a, obs_n, rew, done, info);
+    if (r) return r;
+    a.flags = flags;
+    return launch(h, kObserve, a, stream);
+}
+
+extern "C" int mpe_step(mpe_handle h, void *pv, const void *lm, float *comm, const int32_t *goal,
+                        const float *const *act_n, float *const *obs_n, float *rew, uint8_t *done, float *info,
+                        uint32_t flags, void *stream) {
+    if (!h) return MPE_ERR_BAD_ARG;
+    if (flags & MPE_FLAG_DISCRETE_ACTION_INPUT) return MPE_ERR_UNSUPPORTED;
+    StepArgs a{};
+    int r = fill_state(h, a, pv, lm, comm, goal);
+    if (r) return r;
+    r = fill_actions(h, a, act_n);
+    if (r) return r;
+    r = fill_outputs(h, a, obs_n, rew, done, info);
+    if (r) return r;
+    a.flags = flags;
+    return launch(h, kFusedStep, a, stream);
+}
+
+extern "C" int mpe_step_host(mpe_handle h, void *pv, const void *lm, float *comm, const int32_t *goal,
+                             const float *const *act_n_host, float *const *act_n_dev, float *const *obs_n_dev,
+                             float *rew_dev, uint8_t *done_dev, float *info_dev, float *const *obs_n_host,
+                             float *rew_host, uint8_t *done_host, float *info_host, uint32_t flags, void *stream) {
+    if (!h || !act_n_host || !act_n_dev || !obs_n_host || !obs_n_dev || !rew_host || !done_host) return MPE_ERR_BAD_ARG;
+    if (h->device < 0) return MPE_ERR_NO_DEVICE;
+    const Program *p = h->prog;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int prev = 0;
+    CUDA_TRY(cudaGetDevice(&prev));
+    if (prev != h->device) CUDA_TRY(cudaSetDevice(h->device));
+    int rc = MPE_OK;
+    for (int i = 0; i < p->A && rc == MPE_OK; ++i) {
+        if (!act_n_host[i] || !act_n_dev[i]) { rc = MPE_ERR_BAD_ARG; break; }
+        cudaError_t e = cudaMemcpyAsync(act_n_dev[i], act_n_host[i], sizeof(float) * h->n * p->act_dim[i], cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync(H2D actions)");
+    }
+    if (rc == MPE_OK) rc = mpe_step(h, pv, lm, comm, goal, act_n_dev, obs_n_dev, rew_dev, done_dev, info_dev, flags, stream);
+    for (int i = 0; i < p->A && rc == MPE_OK; ++i) {
+        if (!obs_n_host[i]) { rc = MPE_ERR_BAD_ARG; break; }
+        cudaError_t e = cudaMemcpyAsync(obs_n_host[i], obs_n_dev[i], sizeof(float) * h->n * p->obs_dim[i], cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync(D2H obs)");
+    }
+    if (rc == MPE_OK) {
+        cudaError_t e = cudaMemcpyAsync(rew_host, rew_dev, sizeof(float) * h->n * p->A, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(done_host, done_dev, static_cast<size_t>(h->n) * p->A, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && info_host && info_dev && p->INFO > 0)
+            e = cudaMemcpyAsync(info_host, info_dev, sizeof(float) * h->n * p->A * p->INFO, cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync(D2H rew/done/info)");
+    }
+    if (prev != h->device) cudaSetDevice(prev);
+    return rc;
+}
+
+extern "C" int mpe_reset(mpe_handle h, void *pv, void *lm, float *comm, int32_t *goal, const uint8_t *mask,
+                         uint64_t seed, uint64_t world_offset, uint64_t epoch, void *stream) {
+    if (!h) return MPE_ERR_BAD_ARG;
+    if (h->device < 0) return MPE_ERR_NO_DEVICE;
+    StepArgs tmp{};
+    int r = fill_state(h, tmp, pv, lm, comm, goal);
+    if (r) return r;
+    const Program *p = h->prog;
+    ResetArgs a{};
+    a.n = h->n; a.A = p->A; a.L = p->L; a.NC = p->NS * p->DIMC; a.G = p->G;
+    a.pv = static_cast<float4 *>(pv); a.lm = static_cast<float2 *>(lm); a.comm = comm; a.goal = goal; a.mask = mask;
+    a.seed = seed; a.world_offset = world_offset; a.epoch = epoch;
+    a.agent_range = 1.0f;  // every scenario: agents ~ U(-1, +1)^2
+    // landmarks: U(-1,+1) (simple.py:37, simple_spread.py:44) or U(-0.9,+0.9) (simple_tag.py:53, simple_world_comm.py:105-113)
+    const bool narrow = (p->scenario == MPE_SCN_TAG || p->scenario == MPE_SCN_WORLD_COMM);
+    for (int l = 0; l < kMaxL; ++l) a.landmark_range[l] = narrow ? 0.9f : 1.0f;
+    for (int g = 0; g < 4; ++g) a.goal_mod[g] = p->L > 0 ? p->L : 1;
+    int prev = 0;
+    CUDA_TRY(cudaGetDevice(&prev));
+    if (prev != h->device) CUDA_TRY(cudaSetDevice(h->device));
+    const unsigned blocks = static_cast<unsigned>((h->n + 255) / 256);
+    reset_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (prev != h->device) cudaSetDevice(prev);
+    if (e != cudaSuccess) return cuda_fail(e, "reset_kernel");
+    __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED);
+    return MPE_OK;
+}
+
+extern "C" const char *mpe_strerror(int err) {
+    switch (err) {
+    case MPE_OK: return "ok";
+    case MPE_ERR_BAD_ARG: return "bad argument (null or misaligned pointer, bad size or index)";
+    case MPE_ERR_BAD_DESC: return "descriptor does not fit its scenario program";
+    case MPE_ERR_UNSUPPORTED: return "no compiled sm_100a program for this scenario / shape / flag";
+    case MPE_ERR_CUDA: return "CUDA runtime error (see mpe_last_cuda_error)";
+    case MPE_ERR_NO_DEVICE: return "no sm_100 (B200) device with that index, or shape-only handle (device -1)";
+    default: return "unknown error";
+    }
+}
+extern "C" const char *mpe_last_cuda_error(void) { return g_cuda_err; }
+extern "C" int mpe_abi_version(void) { return MPE_ABI_VERSION; }
+extern "C" int64_t mpe_kernel_launches(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }

@@ -1,0 +1,301 @@
+// mpe_scenarios.cuh -- the scenario programs: observation / reward / benchmark_data of each
+// reference scenario file, written against per-lane world registers.  Entity counts are template
+// parameters so every loop unrolls; entity *properties* (size, collide, ...) stay runtime values
+// read from the constant bank, i.e. whatever Scenario.make_world() put on the World object.
+//
+// A program P provides
+//   A, L, DIMC, NS (#speakers = non-silent agents, the first NS agents), INFO (floats/agent)
+//   obs_dim(i), act_dim(i), movable(i)            constexpr shape functions
+//   observe<I>(d, w, out)                         scenario.observation(agent I, world)
+//   reward(d, w, rew[A], info[A*INFO])            scenario.reward / benchmark_data for every agent
+//   validate(desc)                                host: does the descriptor fit this program?
+#pragma once
+#include "mpe_common.cuh"
+
+namespace mpe {
+
+template <int A_, int L_, int NC_>
+struct WorldRegs {
+    float px[A_], py[A_], vx[A_], vy[A_];
+    float lx[L_], ly[L_];
+    float c[NC_ > 0 ? NC_ : 1];  // comm state of the speakers, [speaker][dim_c]
+};
+
+__host__ __device__ constexpr uint32_t low_bits(int n) { return n >= 32 ? 0xffffffffu : ((1u << n) - 1u); }
+
+// ---------------------------------------------------------------------------------------------
+// simple.py : 1 agent, 1 landmark, nothing collides
+template <int A_, int L_>
+struct Simple {
+    static constexpr int A = A_, L = L_, DIMC = 0, NS = 0, INFO = 0, G = 0;
+    static constexpr int kScenario = MPE_SCN_SIMPLE;
+    using W = WorldRegs<A, L, 0>;
+    __host__ __device__ static constexpr int obs_dim(int) { return 2 + 2 * L; }   // simple.py:45-50
+    __host__ __device__ static constexpr int act_dim(int) { return 5; }
+    __host__ __device__ static constexpr bool movable(int) { return true; }
+
+    template <int I>
+    __device__ __forceinline__ static void observe(const DevDesc &, const W &w, RowWriter &o) {
+        o.put2(w.vx[I], w.vy[I]);                                                    // :50
+#pragma unroll
+        for (int l = 0; l < L; ++l) o.put2(w.lx[l] - w.px[I], w.ly[l] - w.py[I]);    // :48-49
+    }
+    __device__ __forceinline__ static void reward(const DevDesc &, const W &w, float (&rew)[A], float *) {
+#pragma unroll
+        for (int i = 0; i < A; ++i) {
+            const float dx = w.px[i] - w.lx[0], dy = w.py[i] - w.ly[0];
+            rew[i] = -(dx * dx + dy * dy);                                           // :41-43
+        }
+    }
+    static bool validate(const mpe_desc &d) {
+        return d.n_agents == A && d.n_landmarks == L && d.dim_c == 0;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// simple_spread.py : N agents, N landmarks, cooperative
+template <int N_>
+struct Spread {
+    static constexpr int A = N_, L = N_, DIMC = 2, NS = 0, INFO = 4, G = 0;
+    static constexpr int kScenario = MPE_SCN_SPREAD;
+    using W = WorldRegs<A, L, 0>;
+    __host__ __device__ static constexpr int obs_dim(int) { return 4 + 2 * L + 2 * (A - 1) + DIMC * (A - 1); }
+    __host__ __device__ static constexpr int act_dim(int) { return 5; }
+    __host__ __device__ static constexpr bool movable(int) { return true; }
+
+    template <int I>
+    __device__ __forceinline__ static void observe(const DevDesc &, const W &w, RowWriter &o) {
+        o.put2(w.vx[I], w.vy[I]);                                                    // simple_spread.py:100
+        o.put2(w.px[I], w.py[I]);
+#pragma unroll
+        for (int l = 0; l < L; ++l) o.put2(w.lx[l] - w.px[I], w.ly[l] - w.py[I]);    // :87-88
+#pragma unroll
+        for (int j = 0; j < A; ++j)
+            if (j != I) o.put2(w.px[j] - w.px[I], w.py[j] - w.py[I]);                // :99
+#pragma unroll
+        for (int j = 0; j < (A - 1) * DIMC; ++j) o.put(0.0f);                        // :98 (all agents silent)
+    }
+    __device__ __forceinline__ static void reward(const DevDesc &d, const W &w, float (&rew)[A], float *info) {
+        float base = 0.0f, min_dists = 0.0f;
+        int occupied = 0;
+#pragma unroll
+        for (int l = 0; l < L; ++l) {                                                // :75-77
+            float m = dist2d(w.px[0], w.py[0], w.lx[l], w.ly[l]);
+#pragma unroll
+            for (int a = 1; a < A; ++a) m = fminf(m, dist2d(w.px[a], w.py[a], w.lx[l], w.ly[l]));
+            base -= m;
+            min_dists += m;                                                          // :54
+            occupied += (m < 0.1f) ? 1 : 0;                                          // :56-57
+        }
+#pragma unroll
+        for (int i = 0; i < A; ++i) {
+            float r = base;
+            int coll = 0;
+            if ((d.a_collide >> i) & 1u) {                                           // :78-81, a == i included
+#pragma unroll
+                for (int a = 0; a < A; ++a)
+                    if (is_collision(w.px[a], w.py[a], d.a_size[a], w.px[i], w.py[i], d.a_size[i])) {
+                        r -= 1.0f;
+                        coll += 1;
+                    }
+            }
+            rew[i] = r;
+            if (info) {                                                              // benchmark_data :47-63
+                info[i * INFO + 0] = r;
+                info[i * INFO + 1] = static_cast<float>(coll);
+                info[i * INFO + 2] = min_dists;
+                info[i * INFO + 3] = static_cast<float>(occupied);
+            }
+        }
+    }
+    static bool validate(const mpe_desc &d) {
+        if (d.n_agents != A || d.n_landmarks != L || d.dim_c != DIMC) return false;
+        for (int i = 0; i < A; ++i)
+            if (!d.agent_movable[i] || !d.agent_silent[i]) return false;
+        return true;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// simple_tag.py : NADV adversaries (first), NGOOD prey, L obstacles
+template <int NADV_, int NGOOD_, int L_>
+struct Tag {
+    static constexpr int NADV = NADV_, NGOOD = NGOOD_;
+    static constexpr int A = NADV + NGOOD, L = L_, DIMC = 2, NS = 0, INFO = 1, G = 0;
+    static constexpr int kScenario = MPE_SCN_TAG;
+    using W = WorldRegs<A, L, 0>;
+    __host__ __device__ static constexpr bool adversary(int i) { return i < NADV; }
+    __host__ __device__ static constexpr int obs_dim(int i) {                       // simple_tag.py:131-147
+        return 4 + 2 * L + 2 * (A - 1) + 2 * (NGOOD - (adversary(i) ? 0 : 1));
+    }
+    __host__ __device__ static constexpr int act_dim(int) { return 5; }
+    __host__ __device__ static constexpr bool movable(int) { return true; }
+
+    template <int I>
+    __device__ __forceinline__ static void observe(const DevDesc &, const W &w, RowWriter &o) {
+        o.put2(w.vx[I], w.vy[I]);                                                    // :147
+        o.put2(w.px[I], w.py[I]);
+#pragma unroll
+        for (int l = 0; l < L; ++l) o.put2(w.lx[l] - w.px[I], w.ly[l] - w.py[I]);    // :133-136
+#pragma unroll
+        for (int j = 0; j < A; ++j)
+            if (j != I) o.put2(w.px[j] - w.px[I], w.py[j] - w.py[I]);                // :144
+#pragma unroll
+        for (int j = NADV; j < A; ++j)
+            if (j != I) o.put2(w.vx[j], w.vy[j]);                                    // :145-146
+    }
+    __device__ __forceinline__ static void reward(const DevDesc &d, const W &w, float (&rew)[A], float *info) {
+        // every (good, adversary) contact flag once; both reward branches are sums over them
+        bool hit[NGOOD][NADV];
+#pragma unroll
+        for (int g = 0; g < NGOOD; ++g)
+#pragma unroll
+            for (int a = 0; a < NADV; ++a)
+                hit[g][a] = is_collision(w.px[NADV + g], w.py[NADV + g], d.a_size[NADV + g],
+                                         w.px[a], w.py[a], d.a_size[a]);
+#pragma unroll
+        for (int i = 0; i < A; ++i) {
+            float r = 0.0f;
+            int coll = 0;
+            if (adversary(i)) {                                                      // adversary_reward :115-129
+#pragma unroll
+                for (int g = 0; g < NGOOD; ++g) {
+#pragma unroll
+                    for (int a = 0; a < NADV; ++a)
+                        if (((d.a_collide >> i) & 1u) && hit[g][a]) r += 10.0f;
+                    coll += hit[g][i < NADV ? i : 0] ? 1 : 0;                        // benchmark_data :57-66
+                }
+            } else {                                                                 // agent_reward :89-113
+#pragma unroll
+                for (int a = 0; a < NADV; ++a)
+                    if (((d.a_collide >> i) & 1u) && hit[i >= NADV ? i - NADV : 0][a]) r -= 10.0f;
+                r -= bound_pen(fabsf(w.px[i]));                                      // :109-111
+                r -= bound_pen(fabsf(w.py[i]));
+            }
+            rew[i] = r;
+            if (info) info[i] = static_cast<float>(coll);
+        }
+    }
+    static bool validate(const mpe_desc &d) {
+        if (d.n_agents != A || d.n_landmarks != L || d.dim_c != DIMC || d.n_adversaries != NADV) return false;
+        for (int i = 0; i < A; ++i)
+            if (!d.agent_movable[i] || !d.agent_silent[i] || (d.agent_adversary[i] != 0) != adversary(i)) return false;
+        return true;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// simple_world_comm.py : NADV adversaries (agent 0 = leader, the only speaker), NGOOD prey,
+// landmarks = NOBST obstacles ++ NFOOD food ++ 2 forests
+template <int NADV_, int NGOOD_, int NOBST_, int NFOOD_>
+struct WorldComm {
+    static constexpr int NADV = NADV_, NGOOD = NGOOD_, NOBST = NOBST_, NFOOD = NFOOD_, NFOREST = 2;
+    static constexpr int A = NADV + NGOOD, L = NOBST + NFOOD + NFOREST, DIMC = 4, NS = 1, INFO = 1, G = 0;
+    static constexpr int FOOD0 = NOBST, FOREST0 = NOBST + NFOOD;
+    static constexpr int kScenario = MPE_SCN_WORLD_COMM;
+    using W = WorldRegs<A, L, NS * DIMC>;
+    __host__ __device__ static constexpr bool adversary(int i) { return i < NADV; }
+    __host__ __device__ static constexpr int obs_dim(int i) {                       // simple_world_comm.py:281-287
+        return 4 + 2 * L + 2 * (A - 1) + 2 * (NGOOD - (adversary(i) ? 0 : 1)) + 2 + (adversary(i) ? DIMC : 0);
+    }
+    __host__ __device__ static constexpr int act_dim(int i) { return i == 0 ? 5 + DIMC : 5; }
+    __host__ __device__ static constexpr bool movable(int) { return true; }
+
+    __device__ __forceinline__ static bool in_forest(const DevDesc &d, const W &w, int i, int f) {
+        return is_collision(w.px[i], w.py[i], d.a_size[i], w.lx[FOREST0 + f], w.ly[FOREST0 + f],
+                            d.l_size[FOREST0 + f]);                                  // :231-239, 251-252
+    }
+
+    template <int I>
+    __device__ __forceinline__ static void observe(const DevDesc &d, const W &w, RowWriter &o) {
+        o.put2(w.vx[I], w.vy[I]);
+        o.put2(w.px[I], w.py[I]);
+#pragma unroll
+        for (int l = 0; l < L; ++l) o.put2(w.lx[l] - w.px[I], w.ly[l] - w.py[I]);    // :226-229
+        const bool f0 = in_forest(d, w, I, 0), f1 = in_forest(d, w, I, 1);
+        bool vis[A];
+#pragma unroll
+        for (int j = 0; j < A; ++j) {                                                // :253 (leader sees all)
+            const bool g0 = in_forest(d, w, j, 0), g1 = in_forest(d, w, j, 1);
+            vis[j] = (f0 && g0) || (f1 && g1) || (!f0 && !g0 && !f1 && !g1) || (I == 0);
+        }
+#pragma unroll
+        for (int j = 0; j < A; ++j)
+            if (j != I) o.put2(vis[j] ? w.px[j] - w.px[I] : 0.0f, vis[j] ? w.py[j] - w.py[I] : 0.0f);
+        if (adversary(I)) {
+#pragma unroll
+            for (int j = NADV; j < A; ++j)
+                if (j != I) o.put2(vis[j] ? w.vx[j] : 0.0f, vis[j] ? w.vy[j] : 0.0f);
+            o.put2(f0 ? 1.0f : -1.0f, f1 ? 1.0f : -1.0f);
+#pragma unroll
+            for (int q = 0; q < DIMC; ++q) o.put(w.c[q]);                            // :279
+        } else {
+            o.put2(f0 ? 1.0f : -1.0f, f1 ? 1.0f : -1.0f);                            // :287
+#pragma unroll
+            for (int j = NADV; j < A; ++j)
+                if (j != I) o.put2(vis[j] ? w.vx[j] : 0.0f, vis[j] ? w.vy[j] : 0.0f);
+        }
+    }
+    __device__ __forceinline__ static void reward(const DevDesc &d, const W &w, float (&rew)[A], float *info) {
+        bool hit[NGOOD][NADV];
+#pragma unroll
+        for (int g = 0; g < NGOOD; ++g)
+#pragma unroll
+            for (int a = 0; a < NADV; ++a)
+                hit[g][a] = is_collision(w.px[NADV + g], w.py[NADV + g], d.a_size[NADV + g],
+                                         w.px[a], w.py[a], d.a_size[a]);
+#pragma unroll
+        for (int i = 0; i < A; ++i) {
+            float r = 0.0f;
+            int coll = 0;
+            if (adversary(i)) {                                                      // adversary_reward :185-198
+                float m = dist2d(w.px[NADV], w.py[NADV], w.px[i], w.py[i]);
+#pragma unroll
+                for (int g = 1; g < NGOOD; ++g) {
+                    const float dd = dist2d(w.px[NADV + g], w.py[NADV + g], w.px[i], w.py[i]);
+                    m = dd < m ? dd : m;
+                }
+                r -= 0.1f * m;                                                       // :192
+#pragma unroll
+                for (int g = 0; g < NGOOD; ++g) {
+#pragma unroll
+                    for (int a = 0; a < NADV; ++a)
+                        if (((d.a_collide >> i) & 1u) && hit[g][a]) r += 5.0f;       // :193-197
+                    coll += hit[g][i < NADV ? i : 0] ? 1 : 0;                        // benchmark_data :115-123
+                }
+            } else {                                                                 // agent_reward :155-183
+#pragma unroll
+                for (int a = 0; a < NADV; ++a)
+                    if (((d.a_collide >> i) & 1u) && hit[i >= NADV ? i - NADV : 0][a]) r -= 5.0f;
+                r -= 2.0f * bound_pen(fabsf(w.px[i]));                               // :176-178
+                r -= 2.0f * bound_pen(fabsf(w.py[i]));
+#pragma unroll
+                for (int f = 0; f < NFOOD; ++f)                                      // :179-181
+                    if (is_collision(w.px[i], w.py[i], d.a_size[i], w.lx[FOOD0 + f], w.ly[FOOD0 + f],
+                                     d.l_size[FOOD0 + f]))
+                        r += 2.0f;
+                float m = dist2d(w.lx[FOOD0], w.ly[FOOD0], w.px[i], w.py[i]);
+#pragma unroll
+                for (int f = 1; f < NFOOD; ++f) {
+                    const float dd = dist2d(w.lx[FOOD0 + f], w.ly[FOOD0 + f], w.px[i], w.py[i]);
+                    m = dd < m ? dd : m;
+                }
+                r += 0.05f * m;                                                      // :182
+            }
+            rew[i] = r;
+            if (info) info[i] = static_cast<float>(coll);
+        }
+    }
+    static bool validate(const mpe_desc &d) {
+        if (d.n_agents != A || d.n_landmarks != L || d.dim_c != DIMC || d.n_adversaries != NADV) return false;
+        if (d.n_obstacles != NOBST || d.n_food != NFOOD || d.n_forests != NFOREST) return false;
+        for (int i = 0; i < A; ++i) {
+            if (!d.agent_movable[i] || (d.agent_adversary[i] != 0) != adversary(i)) return false;
+            if ((d.agent_leader[i] != 0) != (i == 0)) return false;
+            if ((d.agent_silent[i] == 0) != (i == 0)) return false;
+        }
+        return true;
+    }
+};
+
+}  // namespace mpe

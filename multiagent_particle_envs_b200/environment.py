@@ -1,0 +1,298 @@
+"""MultiAgentEnv: the gym-style adapter over a (batched) World
+(reference: multiagent/environment.py:12-263).
+
+Same constructor, attributes and `step` / `reset` contract as the reference.  The per-agent
+Python loops of the reference's `step` (`_set_action` -> `world.step()` -> observation / reward /
+done / info callbacks -> shared-reward sum, environment.py:80-104) are ONE launch of the fused
+sm_100a kernel (`mpe_step`) over all worlds of the batch.
+
+Calling conventions
+  scalar mode  (world.num_envs is None; what `make_env(name)` gives): identical to the reference --
+      `action_n[i]` is a 1-D array, `obs_n[i]` a float64 ndarray, `reward_n[i]` a float,
+      `done_n[i]` a bool, `info_n == {'n': [...]}`.
+  batched mode (world.num_envs = N): `action_n[i]` is `[N, act_dim_i]`; CUDA tensors in ->
+      CUDA tensors out (`obs_n[i]: [N, obs_dim_i]`, `reward_n[i]: [N]`, `done_n[i]: [N] bool`);
+      NumPy arrays / CPU tensors in -> the step runs through pinned staging (`mpe_step_host`) and
+      NumPy arrays / CPU tensors come back.
+"""
+import numpy as np
+
+from . import _lib
+from .multi_discrete import MultiDiscrete
+from .scenario import NativeScenario
+from . import spaces
+
+try:  # pragma: no cover
+    from gym import Env as _Env
+except Exception:  # noqa: BLE001
+    class _Env(object):
+        pass
+
+
+class MultiAgentEnv(_Env):
+    metadata = {'render.modes': ['human', 'rgb_array']}
+
+    def __init__(self, world, reset_callback=None, reward_callback=None,
+                 observation_callback=None, info_callback=None,
+                 done_callback=None, shared_viewer=True):
+        self.world = world
+        self.agents = self.world.policy_agents
+        self.n = len(world.policy_agents)
+        self.reset_callback = reset_callback
+        self.reward_callback = reward_callback
+        self.observation_callback = observation_callback
+        self.info_callback = info_callback
+        self.done_callback = done_callback
+        # environment parameters (environment.py:28-36)
+        self.discrete_action_space = True
+        self.discrete_action_input = False
+        self.force_discrete_action = world.discrete_action if hasattr(world, 'discrete_action') else False
+        self.shared_reward = world.collaborative if hasattr(world, 'collaborative') else False
+        self.time = 0
+        #: batched CUDA mode only: write every step into the same output tensors instead of
+        #: returning freshly allocated ones (zero allocations per step; outputs alias across steps)
+        self.reuse_buffers = False
+
+        for name, cb in (("reward_callback", reward_callback), ("observation_callback", observation_callback)):
+            owner = getattr(cb, "__self__", None)
+            if cb is not None and not isinstance(owner, NativeScenario):
+                raise NotImplementedError(
+                    "%s is an arbitrary Python callable; only scenarios with a compiled sm_100a program "
+                    "(subclasses of NativeScenario) can be stepped, and there is no CPU fallback" % name)
+        self._native_info = info_callback is not None and isinstance(getattr(info_callback, "__self__", None),
+                                                                     NativeScenario)
+        shapes = world.native_shapes()   # validates the descriptor; works without a GPU
+        if shapes.n_agents != self.n:
+            raise ValueError("native program agent count mismatch")
+
+        # configure spaces (environment.py:39-70)
+        self.action_space = []
+        self.observation_space = []
+        for i, agent in enumerate(self.agents):
+            total_action_space = []
+            if agent.movable:
+                total_action_space.append(spaces.Discrete(world.dim_p * 2 + 1))
+            if not agent.silent:
+                total_action_space.append(spaces.Discrete(world.dim_c))
+            if len(total_action_space) > 1:
+                self.action_space.append(MultiDiscrete([[0, sp.n - 1] for sp in total_action_space]))
+            else:
+                self.action_space.append(total_action_space[0])
+            self.observation_space.append(spaces.Box(low=-np.inf, high=+np.inf, shape=(shapes.obs_dims[i],),
+                                                     dtype=np.float32))
+        self._act_dims = list(shapes.act_dims)
+        self._sub_sizes = [([5] if a.movable else []) + ([world.dim_c] if not a.silent else []) for a in self.agents]
+
+        # rendering (no GUI on this path; attributes kept for API compatibility)
+        self.shared_viewer = shared_viewer
+        self.viewers = [None] if shared_viewer else [None] * self.n
+        self._reset_render()
+
+    # ------------------------------------------------------------------------------------------
+    def _flags(self):
+        f = 0
+        if self.shared_reward:
+            f |= _lib.FLAG_SHARED_REWARD
+        if self.force_discrete_action:
+            f |= _lib.FLAG_FORCE_DISCRETE_ACTION
+        if not self.discrete_action_space:
+            raise NotImplementedError("discrete_action_space=False is not supported (hard-coded True in the "
+                                      "reference, environment.py:29)")
+        return f
+
+    def _onehot_from_indices(self, action_n):
+        """discrete_action_input (environment.py:161-167,185-187): integer sub-actions -> the
+        one-hot vectors the kernel decodes.  Note the reference maps index 1 -> u.x = -1 but
+        one-hot position 1 -> u.x = +1; the permutation below preserves the index semantics."""
+        import torch
+        perm = [0, 2, 1, 4, 3]
+        out = []
+        N = self.world.batch_size
+        dev = self.world.bind().device
+        for i, a in enumerate(action_n):
+            idx = torch.as_tensor(np.asarray(a) if not torch.is_tensor(a) else a, device=dev).reshape(N, -1).long()
+            parts, col = [], 0
+            for k, size in enumerate(self._sub_sizes[i]):
+                v = idx[:, col]
+                if size == 5 and self.agents[i].movable and k == 0:
+                    v = torch.tensor(perm, device=dev)[v]
+                parts.append(torch.nn.functional.one_hot(v, size).float())
+                col += 1
+            out.append(torch.cat(parts, dim=1).contiguous())
+        return out
+
+    def step(self, action_n):
+        world = self.world
+        nw = world.bind()
+        self.agents = world.policy_agents
+        if len(action_n) != self.n:
+            raise ValueError("expected %d actions, got %d" % (self.n, len(action_n)))
+        flags = self._flags()
+        if self.discrete_action_input:
+            action_n = self._onehot_from_indices(action_n)
+        mode, payload = self._classify(action_n, nw)
+        if mode == "cuda":
+            out = nw.out if self.reuse_buffers else nw.new_outputs()
+            nw.step(_lib.ptr_array([t.data_ptr() for t in payload]), out, flags)
+            self._last_out = out
+            world._obs_valid = False
+            return self._pack_batched(nw, out, payload)
+        # host callers: pinned staging -> mpe_step_host -> pinned outputs
+        hs = nw.host_staging()
+        ptrs = []
+        for i, a in enumerate(payload):
+            if mode == "pinned":
+                ptrs.append(a.data_ptr())
+            else:
+                hs["host_act"][i].copy_(a if hasattr(a, "dim") else self._to_cpu_tensor(a, i))
+                ptrs.append(hs["host_act"][i].data_ptr())
+        hout = nw.step_host(_lib.ptr_array(ptrs), flags)
+        nw.torch.cuda.current_stream(nw.device).synchronize()
+        self._last_out = hout
+        world._obs_valid = False
+        if not world.batched:
+            return self._pack_scalar(nw, hout)
+        as_numpy = not hasattr(action_n[0], "dim")
+        return self._pack_batched(nw, hout, None, as_numpy=as_numpy)
+
+    # ---- input classification ---------------------------------------------------------------
+    def _to_cpu_tensor(self, a, i):
+        import torch
+        t = torch.as_tensor(np.ascontiguousarray(np.asarray(a, dtype=np.float32)))
+        return t.reshape(self.world.batch_size, self._act_dims[i])
+
+    def _classify(self, action_n, nw):
+        import torch
+        N = self.world.batch_size
+        if all(torch.is_tensor(a) and a.is_cuda for a in action_n):
+            payload = []
+            for i, a in enumerate(action_n):
+                if a.shape != (N, self._act_dims[i]):
+                    raise ValueError("action_n[%d] must have shape (%d, %d), got %s" %
+                                     (i, N, self._act_dims[i], tuple(a.shape)))
+                if a.dtype != torch.float32 or not a.is_contiguous() or a.data_ptr() % 16:
+                    a = a.to(torch.float32).contiguous().clone()
+                payload.append(a)
+            return "cuda", payload
+        payload = []
+        pinned = True
+        for i, a in enumerate(action_n):
+            if torch.is_tensor(a):
+                a = a.detach()
+                if a.is_cuda:
+                    a = a.cpu()
+                a = a.reshape(N, -1)
+                ok = a.dtype == torch.float32 and a.is_contiguous() and a.is_pinned()
+                if not ok:
+                    a = a.to(torch.float32).contiguous()
+                pinned = pinned and ok
+            else:
+                a = self._to_cpu_tensor(a, i)
+                pinned = False
+            if a.shape != (N, self._act_dims[i]):
+                raise ValueError("action_n[%d] must have %d x %d elements, got shape %s" %
+                                 (i, N, self._act_dims[i], tuple(a.shape)))
+            payload.append(a)
+        return ("pinned" if pinned else "host"), payload
+
+    # ---- output packing -----------------------------------------------------------------------
+    def _info_list(self, nw, out, batched):
+        if self.info_callback is None:
+            return [{} for _ in range(self.n)]
+        if self._native_info:
+            return [nw.benchmark_data(i, batched, out) for i in range(self.n)]
+        return [self.info_callback(agent, self.world) for agent in self.agents]
+
+    def _pack_batched(self, nw, out, _inputs, as_numpy=False):
+        import torch
+        obs_n = list(out.obs)
+        reward_n = [out.rew[i] for i in range(self.n)]
+        done_b = out.done.view(torch.bool)
+        done_n = [done_b[i] for i in range(self.n)]
+        if self.done_callback is not None:
+            done_n = [self.done_callback(agent, self.world) for agent in self.agents]
+        info_n = {'n': self._info_list(nw, out, True)}
+        if as_numpy:
+            obs_n = [o.numpy() for o in obs_n]
+            reward_n = [r.numpy() for r in reward_n]
+            done_n = [d.numpy() if hasattr(d, "numpy") else d for d in done_n]
+        return obs_n, reward_n, done_n, info_n
+
+    def _pack_scalar(self, nw, hout):
+        obs_n = [o[0].numpy().astype(np.float64) for o in hout.obs]
+        rew = hout.rew[:, 0].numpy().astype(np.float64)
+        reward_n = [rew[i] for i in range(self.n)]
+        done_n = [bool(hout.done[i, 0]) for i in range(self.n)]
+        if self.done_callback is not None:
+            done_n = [self.done_callback(agent, self.world) for agent in self.agents]
+        info_n = {'n': self._info_list(nw, hout, False)}
+        return obs_n, reward_n, done_n, info_n
+
+    # ------------------------------------------------------------------------------------------
+    def reset(self, mask=None, seed=None):
+        """environment.py:106-116.  `mask` ([N] bool) resets a subset of the worlds (batched
+        extension); observations are returned for every world."""
+        world = self.world
+        nw = world.bind()
+        if mask is None and seed is None:
+            self.reset_callback(world)
+        else:
+            self.reset_callback(world, mask=mask, seed=seed)
+        self._reset_render()
+        self.agents = world.policy_agents
+        out = nw.out if (self.reuse_buffers or not world.batched) else nw.new_outputs()
+        nw.observe(out, 0)
+        world._obs_valid = False
+        if world.batched:
+            return list(out.obs)
+        return [o[0].detach().to("cpu").numpy().astype(np.float64) for o in out.obs]
+
+    # ---- per-agent accessors kept for API compatibility (environment.py:119-141) --------------
+    def _get_info(self, agent):
+        if self.info_callback is None:
+            return {}
+        return self.info_callback(agent, self.world)
+
+    def _get_obs(self, agent):
+        if self.observation_callback is None:
+            return np.zeros(0)
+        return self.observation_callback(agent, self.world)
+
+    def _get_done(self, agent):
+        if self.done_callback is None:
+            return False
+        return self.done_callback(agent, self.world)
+
+    def _get_reward(self, agent):
+        if self.reward_callback is None:
+            return 0.0
+        return self.reward_callback(agent, self.world)
+
+    def _set_action(self, action, agent, action_space, time=None):
+        """environment.py:144-192 for ONE agent: decodes into agent.action.u / .c via the native
+        set_action kernel (all agents are decoded; the other agents' inputs are zero)."""
+        import torch
+        nw = self.world.bind()
+        idx = self.world._agent_index(agent)
+        acts = [torch.zeros(nw.n_env, ad, device=nw.device) for ad in self._act_dims]
+        acts[idx] = torch.as_tensor(np.asarray(action, dtype=np.float32) if not torch.is_tensor(action) else action,
+                                    dtype=torch.float32, device=nw.device).reshape(nw.n_env, -1).contiguous()
+        keep_u, keep_c = nw.act_u.clone(), nw.act_c.clone()
+        nw.set_action(_lib.ptr_array([t.data_ptr() for t in acts]), self._flags())
+        s = nw.speaker_slot(idx)
+        new_u = nw.act_u[idx].clone()
+        new_c = nw.act_c[s * nw.dim_c:(s + 1) * nw.dim_c].clone() if s >= 0 else None
+        nw.act_u.copy_(keep_u)
+        nw.act_c.copy_(keep_c)
+        nw.act_u[idx] = new_u
+        if new_c is not None:
+            nw.act_c[s * nw.dim_c:(s + 1) * nw.dim_c] = new_c
+
+    # ---- rendering: out of scope on this path ---------------
+    def _reset_render(self):
+        self.render_geoms = None
+        self.render_geoms_xform = None
+
+    def render(self, mode='human'):
+        raise NotImplementedError("rendering (pyglet) is outside the B200 hot path; use the reference's viewer "
+                                  "on states read back through entity.state.p_pos")

@@ -1,0 +1,138 @@
+"""TEST INFRASTRUCTURE ONLY -- never imported by the product package.
+
+Imports the *unmodified* Python reference from /root/reference in this container so that
+(a) the C oracle restatement (oracle/mpe_oracle.c) can be pinned against it and
+(b) golden input/output fixtures can be generated (tests/golden/make_golden.py).
+
+The reference needs `gym` (not installed) and the stdlib module `imp` (removed in 3.12) only for
+type scaffolding, never for arithmetic; the stubs below provide exactly the names it touches
+(SURVEY.md section 8(c)):  gym.Env, gym.Space, gym.spaces.{Discrete,Box,Tuple,prng},
+gym.envs.registration.{register,EnvSpec}, imp.load_source.
+
+/root/reference does not exist on the GPU box: nothing under tests/ -m gpu, smoke() or bench.py
+may import this module.
+"""
+import importlib.machinery
+import importlib.util
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("MPE_REFERENCE_ROOT", "/root/reference")
+
+
+def available():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "multiagent"))
+
+
+def _install_stubs():
+    import numpy as np
+
+    if "gym" not in sys.modules:
+        gym = types.ModuleType("gym")
+
+        class Env(object):
+            pass
+
+        class Space(object):
+            pass
+
+        gym.Env = Env
+        gym.Space = Space
+        spaces = types.ModuleType("gym.spaces")
+
+        class Discrete(Space):
+            def __init__(self, n):
+                self.n = n
+
+        class Box(Space):
+            def __init__(self, low, high, shape=None, dtype=None):
+                self.low, self.high, self.shape, self.dtype = low, high, shape, dtype
+
+        class Tuple(Space):
+            def __init__(self, spaces_):
+                self.spaces = spaces_
+
+        spaces.Discrete, spaces.Box, spaces.Tuple = Discrete, Box, Tuple
+        prng = types.ModuleType("gym.spaces.prng")
+        prng.np_random = np.random.RandomState(0)
+        spaces.prng = prng
+        envs = types.ModuleType("gym.envs")
+        registration = types.ModuleType("gym.envs.registration")
+        registration.register = lambda *a, **k: None
+
+        class EnvSpec(object):
+            pass
+
+        registration.EnvSpec = EnvSpec
+        envs.registration = registration
+        gym.spaces, gym.envs = spaces, envs
+        sys.modules.update({
+            "gym": gym, "gym.spaces": spaces, "gym.spaces.prng": prng,
+            "gym.envs": envs, "gym.envs.registration": registration,
+        })
+    if "imp" not in sys.modules:
+        imp = types.ModuleType("imp")
+
+        def load_source(name, pathname):
+            loader = importlib.machinery.SourceFileLoader(name or "_ref_scenario", pathname)
+            spec = importlib.util.spec_from_loader(loader.name, loader)
+            mod = importlib.util.module_from_spec(spec)
+            loader.exec_module(mod)
+            return mod
+
+        imp.load_source = load_source
+        sys.modules["imp"] = imp
+
+
+def import_reference():
+    """Returns (make_env, multiagent) of the real reference.  Raises if it is not mounted."""
+    if not available():
+        raise RuntimeError("reference not mounted at %s" % REFERENCE_ROOT)
+    os.environ["SUPPRESS_MA_PROMPT"] = "1"
+    _install_stubs()
+    # the product ships a drop-in package that is also called `multiagent`; make sure the
+    # reference's own package wins inside this (test-only) process
+    for k in [k for k in sys.modules if k == "multiagent" or k.startswith("multiagent.") or k == "make_env"]:
+        del sys.modules[k]
+    if REFERENCE_ROOT in sys.path:
+        sys.path.remove(REFERENCE_ROOT)
+    sys.path.insert(0, REFERENCE_ROOT)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        import multiagent  # noqa: F401  (the reference's)
+        import make_env as ref_make_env
+    assert multiagent.__file__.startswith(REFERENCE_ROOT), multiagent.__file__
+    return ref_make_env.make_env, multiagent
+
+
+def make_reference_env(name, n=None):
+    """Reference env for `name`; `simple_spread` accepts n (agents = landmarks = n) by building
+    the world test-side with the reference's own property assignments (simple_spread.py:15-26)
+    and reusing its generic reset_world / reward / observation (SURVEY.md 8(c) "N=6 spread")."""
+    make_env, multiagent = import_reference()
+    if name == "simple_spread" and n not in (None, 3):
+        from multiagent.core import World, Agent, Landmark
+        from multiagent.environment import MultiAgentEnv
+        import multiagent.scenarios as scenarios
+        scenario = scenarios.load("simple_spread.py").Scenario()
+        world = World()
+        world.dim_c = 2
+        world.collaborative = True
+        world.agents = [Agent() for _ in range(n)]
+        for i, agent in enumerate(world.agents):
+            agent.name = "agent %d" % i
+            agent.collide = True
+            agent.silent = True
+            agent.size = 0.15
+        world.landmarks = [Landmark() for _ in range(n)]
+        for i, landmark in enumerate(world.landmarks):
+            landmark.name = "landmark %d" % i
+            landmark.collide = False
+            landmark.movable = False
+        scenario.reset_world(world)
+        return MultiAgentEnv(world, scenario.reset_world, scenario.reward, scenario.observation,
+                             scenario.benchmark_data)
+    return make_env(name, benchmark=(name not in ("simple", "simple_push", "simple_reference",
+                                                  "simple_speaker_listener")))
