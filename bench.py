@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/sec of the multiagent-particle-envs hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W              # this repo (sm_100a kernels)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU arm: the oracle port on host cores
+
+A "step" is one pass of the hot path (MultiAgentEnv.step: action decode -> World.step -> observation /
+reward / done, environment.py:80-104) over ONE batch of `n_env` worlds = one fused-kernel launch.
+Workload (BASELINE.json configs[1]): simple_spread N=3, 65 536 worlds per GPU.  Under torchrun every
+rank steps its own 65 536-world shard (weak scaling, no data-path collective); the only exchange is one
+all-gather of the (env_steps, seconds) counters.
+
+Timing hygiene: the timed steps rotate over a ring of R independent batches whose combined working set
+is > 2x the 126 MB L2 ("inputs larger than L2"); W >= 3 warm-up steps; CUDA events on the launching
+stream with a barrier + synchronize on both sides; max over ranks; nvidia-smi clocks sampled during the
+timed region.  Episodes are reset every 25 steps of each batch (MADDPG's episode length).
+
+value      device-resident throughput: inputs already in HBM, K fused launches replayed from CUDA graphs
+e2e        the same metric through the public API `env.step(host actions)`: pinned H2D of the actions,
+           the fused step, D2H of observations / rewards / dones, every step (mpe_step_host)
+roofline   achieved = algorithmic bytes per launch (411 B x n_env) / mean launch time
+cpu_baseline  the CPU oracle port (oracle/mpe_oracle.c, fp64 like the reference) on all host threads
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SCENARIO = "simple_spread"
+N_ENV = 65536
+EPISODE = 25
+L2_BYTES = 126 * 1024 * 1024
+METRIC = "env_steps_per_sec"
+UNIT = "env-steps/s"
+
+
+def workload_config(n_gpus, ring):
+    return {"workload": "simple_spread N=3 agents/landmarks, batch=65536 worlds per GPU (BASELINE configs[1])",
+            "scenario": SCENARIO, "n_env_per_gpu": N_ENV, "global_n_env": N_ENV * n_gpus,
+            "agents": 3, "episode_length": EPISODE, "ring_batches": ring,
+            "l2_policy": ("inputs larger than L2: steps rotate over %d independent batches (%.0f MB > 2x126 MB)"
+                          % (ring, ring * N_ENV * 411 / 1e6)) if ring > 1 else "n/a (CPU arm)",
+            "actions": "softmax of N(0,1) logits, pre-generated per batch, resident in HBM",
+            "parallelism": "dp%d (independent shards, no data-path collective)" % n_gpus}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for _, r in self.rows[-3:]]
+        sm = sorted(float(r[1]) for r in rows if len(r) > 2 and r[1].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in rows if len(r) >= 9 for k in range(4) if r[5 + k].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": float(rows[0][2]) if rows and len(rows[0]) > 2 else None,
+                "power_w_max": max([float(r[3]) for r in rows if len(r) > 3 and r[3].replace(".", "").isdigit()] or [0.0]),
+                "samples": len(rows), "reasons": reasons}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on all host threads
+# ------------------------------------------------------------------------------------------------
+def cpu_oracle_throughput(budget_s, n_sample=N_ENV, steps=None):
+    """env-steps/s of oracle/mpe_oracle.c (fp64, the reference's arithmetic) stepping `n_sample`
+    simple_spread worlds, the batch split over all host threads (ctypes releases the GIL)."""
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from oracle import Oracle
+    from multiagent_particle_envs_b200 import make_env
+    desc = make_env(SCENARIO).world.descriptor()
+    cores = len(os.sched_getaffinity(0))
+    rng = np.random.RandomState(0)
+    A, L = 3, 3
+    chunks = []
+    per = (n_sample + cores - 1) // cores
+    for c in range(cores):
+        m = min(per, n_sample - c * per)
+        if m <= 0:
+            break
+        pv = np.zeros((m, A, 4))
+        pv[:, :, :2] = rng.uniform(-1, 1, (m, A, 2))
+        lm = rng.uniform(-1, 1, (m, L, 2))
+        logits = rng.randn(m, A, 5)
+        act = np.exp(logits) / np.exp(logits).sum(-1, keepdims=True)
+        chunks.append([Oracle(desc, "f64"), pv, lm, np.zeros((m, A, 2)), act.reshape(m, 15)])
+
+    def run(ch):
+        orc, pv, lm, comm, act = ch
+        ch[1], ch[3], *_ = orc.step(pv, lm, comm, act, flags=1)
+
+    pool = ThreadPoolExecutor(len(chunks))
+    list(pool.map(run, chunks))  # warm-up
+    t0 = time.perf_counter()
+    list(pool.map(run, chunks))
+    one = time.perf_counter() - t0
+    if steps is None:
+        steps = max(1, min(2000, int(budget_s / max(one, 1e-6))))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        list(pool.map(run, chunks))
+    dt = time.perf_counter() - t0
+    pool.shutdown()
+    return {"value": n_sample * steps / dt, "unit": UNIT, "cores": len(chunks), "kind": "port",
+            "sample": "%d steps x %d worlds of the same workload through oracle/mpe_oracle.c (fp64 C restatement of "
+                      "the reference's NumPy path, one thread per core); %.1f s" % (steps, n_sample, dt),
+            "seconds": dt, "steps": steps, "n_sample": n_sample}
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    t_all = time.perf_counter()
+    probe = cpu_oracle_throughput(1.0, steps=2)
+    total = args.steps + args.warmup
+    # bounded sample per step so that the whole K+W run stays within ~90 s
+    n_sample = int(max(256, min(N_ENV, probe["value"] * 90.0 / max(total, 1))))
+    res = cpu_oracle_throughput(0, n_sample=n_sample, steps=args.warmup) if args.warmup else None
+    res = cpu_oracle_throughput(0, n_sample=n_sample, steps=args.steps)
+    cb = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * res["seconds"] / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.gpus, 1), "cpu_baseline": cb,
+            "agent_steps_per_sec": 3 * res["value"],
+            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.perf_counter() - t_all,
+            "note": "reference arm = CPU oracle port (the Python reference cannot travel to the GPU box); each step "
+                    "is a %d-world sample of the 65536-world batch" % n_sample}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_b200_arm(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from multiagent_particle_envs_b200 import _lib, make_env
+    from multiagent_particle_envs_b200.sharding import aggregate_counters
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    # ---- ring of independent batches, each with resident actions and outputs -------------------
+    bytes_per_step = None
+    ring = []
+    R = args.ring
+    for b in range(R):
+        env = make_env(SCENARIO, num_envs=N_ENV * world, device=dev, seed=1000 + b, rank=rank, world_size=world)
+        env.reset()
+        nw = env.world.native
+        bytes_per_step = nw.bytes_per_env_step * N_ENV
+        g = torch.Generator(device=dev).manual_seed(7 * b + rank)
+        acts = [torch.softmax(torch.randn(N_ENV, 5, device=dev, generator=g), 1).contiguous() for _ in range(env.n)]
+        ring.append((env, nw, acts, _lib.ptr_array([t.data_ptr() for t in acts]), env._flags()))
+    assert R * bytes_per_step > 2 * L2_BYTES, "ring working set must exceed 2x L2"
+    stream = torch.cuda.Stream(dev)
+    launches = [0]
+
+    def step_ring_once():
+        for env, nw, acts, ptrs, flags in ring:
+            nw.step(ptrs, nw.out, flags)
+            launches[0] += 1
+
+    def reset_ring():
+        for env, nw, acts, ptrs, flags in ring:
+            nw.reset()
+            launches[0] += 1
+
+    unit_steps = R * EPISODE
+    with torch.cuda.stream(stream):
+        step_ring_once()  # first launches outside capture (module load)
+        stream.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        l0 = launches[0]
+        with torch.cuda.graph(graph, stream=stream):
+            for _ in range(EPISODE):
+                step_ring_once()
+        launches[0] = l0  # capture is not execution
+
+        def run_steps(k):
+            """exactly k fused steps: whole episodes from the graph (+ the episode resets), then the rest"""
+            units, rem = divmod(k, unit_steps)
+            for _ in range(units):
+                graph.replay()
+                launches[0] += unit_steps
+                reset_ring()
+            i = 0
+            while rem > 0:
+                env, nw, acts, ptrs, flags = ring[i % R]
+                nw.step(ptrs, nw.out, flags)
+                launches[0] += 1
+                i += 1
+                rem -= 1
+
+        run_steps(max(args.warmup, 3))
+        stream.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local_rank).start()
+        time.sleep(0.12)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches[0] = 0
+        t0 = time.time()
+        e0.record(stream)
+        run_steps(args.steps)
+        e1.record(stream)
+        stream.synchronize()
+        t1 = time.time()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        clocks = sampler.stop(t0, t1)
+        seconds = e0.elapsed_time(e1) / 1e3
+    gpu_launches = launches[0]
+    total_steps, max_seconds, per_rank = aggregate_counters(N_ENV * args.steps, seconds)
+    value = total_steps / max_seconds
+
+    # ---- end to end through the public API with host buffers ------------------------------------
+    env, nw = ring[0][0], ring[0][1]
+    k_e2e = max(3, min(args.steps, args.e2e_steps))
+    host_acts = [[a.cpu().pin_memory() for a in ring[b % R][2]] for b in range(4)]
+    h2d = sum(a.numel() * 4 for a in host_acts[0])
+    for b in range(3):
+        obs_n, rew_n, done_n, _ = env.step(host_acts[b % 4])
+    d2h = sum(o.numel() * 4 for o in obs_n) + sum(r.numel() * 4 for r in rew_n) + sum(d.numel() for d in done_n)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    checksum = 0.0
+    w0 = time.perf_counter()
+    for b in range(k_e2e):
+        obs_n, rew_n, done_n, _ = env.step(host_acts[b % 4])   # H2D + fused step + D2H + sync inside
+        checksum += float(rew_n[0][0])                          # the caller reads the result on the host
+    torch.cuda.synchronize()
+    e2e_seconds = time.perf_counter() - w0
+    e2e_total, e2e_max, _ = aggregate_counters(N_ENV * k_e2e, e2e_seconds)
+    e2e_value = e2e_total / e2e_max
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        launch_s = max_seconds / args.steps
+        achieved = bytes_per_step / launch_s / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("simple_spread_65536_dram_bytes_per_launch")
+            except Exception:  # noqa: BLE001
+                traffic = None
+        cpu = cpu_oracle_throughput(args.cpu_seconds) if world == 1 and args.cpu_seconds > 0 else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": 1e3 * launch_s, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(world, R),
+            "agent_steps_per_sec": 3 * value,
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": k_e2e, "ms_per_step": 1e3 * e2e_max / k_e2e, "api": "MultiAgentEnv.step(pinned host tensors)"},
+            "gpu_launches": gpu_launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bytes_per_step, "kernel": "mpe_kernel<Spread<3>, kFusedStep>"},
+            "per_rank": per_rank,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=60000)
+    ap.add_argument("--warmup", type=int, default=3000)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ring", type=int, default=12)
+    ap.add_argument("--e2e-steps", type=int, default=200)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1 and args.gpus > 1 and args.impl == "b200":
+        # convenience: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(29400 + os.getpid() % 500), os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    import __graft_entry__ as g
+    g.build(quiet=True)
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+    else:
+        run_b200_arm(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -562,6 +562,24 @@ extern "C" int mpe_step(mpe_handle h, void *pv, const void *lm, float *comm, con
     return launch(h, kFusedStep, a, stream);
 }
 
+// adjacent (dst, src, bytes) copies with equal small gaps on both sides are issued as one DMA
+struct CopySeg { char *dst; const char *src; size_t bytes; };
+static int issue_copies(CopySeg *seg, int n, cudaMemcpyKind kind, cudaStream_t s, const char *what) {
+    int i = 0;
+    while (i < n) {
+        CopySeg cur = seg[i++];
+        while (i < n) {
+            const ptrdiff_t gd = seg[i].dst - (cur.dst + cur.bytes), gs = seg[i].src - (cur.src + cur.bytes);
+            if (gd != gs || gd < 0 || gd >= 512) break;
+            cur.bytes += static_cast<size_t>(gd) + seg[i].bytes;
+            ++i;
+        }
+        cudaError_t e = cudaMemcpyAsync(cur.dst, cur.src, cur.bytes, kind, s);
+        if (e != cudaSuccess) return cuda_fail(e, what);
+    }
+    return MPE_OK;
+}
+
 extern "C" int mpe_step_host(mpe_handle h, void *pv, const void *lm, float *comm, const int32_t *goal,
                              const float *const *act_n_host, float *const *act_n_dev, float *const *obs_n_dev,
                              float *rew_dev, uint8_t *done_dev, float *info_dev, float *const *obs_n_host,
@@ -570,27 +588,33 @@ extern "C" int mpe_step_host(mpe_handle h, void *pv, const void *lm, float *comm
     if (h->device < 0) return MPE_ERR_NO_DEVICE;
     const Program *p = h->prog;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t n = static_cast<size_t>(h->n);
+    CopySeg seg[kMaxA + 3];
+    int ns = 0;
+    for (int i = 0; i < p->A; ++i) {
+        if (!act_n_host[i] || !act_n_dev[i] || !obs_n_host[i] || !obs_n_dev[i]) return MPE_ERR_BAD_ARG;
+        seg[ns++] = {reinterpret_cast<char *>(act_n_dev[i]), reinterpret_cast<const char *>(act_n_host[i]),
+                     sizeof(float) * n * p->act_dim[i]};
+    }
     int prev = 0;
     CUDA_TRY(cudaGetDevice(&prev));
     if (prev != h->device) CUDA_TRY(cudaSetDevice(h->device));
-    int rc = MPE_OK;
-    for (int i = 0; i < p->A && rc == MPE_OK; ++i) {
-        if (!act_n_host[i] || !act_n_dev[i]) { rc = MPE_ERR_BAD_ARG; break; }
-        cudaError_t e = cudaMemcpyAsync(act_n_dev[i], act_n_host[i], sizeof(float) * h->n * p->act_dim[i], cudaMemcpyHostToDevice, s);
-        if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync(H2D actions)");
-    }
-    if (rc == MPE_OK) rc = mpe_step(h, pv, lm, comm, goal, act_n_dev, obs_n_dev, rew_dev, done_dev, info_dev, flags, stream);
-    for (int i = 0; i < p->A && rc == MPE_OK; ++i) {
-        if (!obs_n_host[i]) { rc = MPE_ERR_BAD_ARG; break; }
-        cudaError_t e = cudaMemcpyAsync(obs_n_host[i], obs_n_dev[i], sizeof(float) * h->n * p->obs_dim[i], cudaMemcpyDeviceToHost, s);
-        if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync(D2H obs)");
-    }
+    int rc = issue_copies(seg, ns, cudaMemcpyHostToDevice, s, "cudaMemcpyAsync(H2D actions)");
+    const bool want_info = info_host && info_dev && p->INFO > 0;
+    if (rc == MPE_OK)
+        rc = mpe_step(h, pv, lm, comm, goal, act_n_dev, obs_n_dev, rew_dev, done_dev, want_info ? info_dev : nullptr,
+                      flags, stream);
     if (rc == MPE_OK) {
-        cudaError_t e = cudaMemcpyAsync(rew_host, rew_dev, sizeof(float) * h->n * p->A, cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(done_host, done_dev, static_cast<size_t>(h->n) * p->A, cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess && info_host && info_dev && p->INFO > 0)
-            e = cudaMemcpyAsync(info_host, info_dev, sizeof(float) * h->n * p->A * p->INFO, cudaMemcpyDeviceToHost, s);
-        if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync(D2H rew/done/info)");
+        ns = 0;
+        for (int i = 0; i < p->A; ++i)
+            seg[ns++] = {reinterpret_cast<char *>(obs_n_host[i]), reinterpret_cast<const char *>(obs_n_dev[i]),
+                         sizeof(float) * n * p->obs_dim[i]};
+        seg[ns++] = {reinterpret_cast<char *>(rew_host), reinterpret_cast<const char *>(rew_dev), sizeof(float) * n * p->A};
+        seg[ns++] = {reinterpret_cast<char *>(done_host), reinterpret_cast<const char *>(done_dev), n * p->A};
+        if (want_info)
+            seg[ns++] = {reinterpret_cast<char *>(info_host), reinterpret_cast<const char *>(info_dev),
+                         sizeof(float) * n * p->A * p->INFO};
+        rc = issue_copies(seg, ns, cudaMemcpyDeviceToHost, s, "cudaMemcpyAsync(D2H obs/rew/done/info)");
     }
     if (prev != h->device) cudaSetDevice(prev);
     return rc;

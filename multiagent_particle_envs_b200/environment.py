@@ -133,7 +133,7 @@ class MultiAgentEnv(_Env):
         mode, payload = self._classify(action_n, nw)
         if mode == "cuda":
             out = nw.out if self.reuse_buffers else nw.new_outputs()
-            nw.step(_lib.ptr_array([t.data_ptr() for t in payload]), out, flags)
+            nw.step(_lib.ptr_array([t.data_ptr() for t in payload]), out, flags, with_info=self._native_info)
             self._last_out = out
             world._obs_valid = False
             return self._pack_batched(nw, out, payload)
@@ -146,7 +146,7 @@ class MultiAgentEnv(_Env):
             else:
                 hs["host_act"][i].copy_(a if hasattr(a, "dim") else self._to_cpu_tensor(a, i))
                 ptrs.append(hs["host_act"][i].data_ptr())
-        hout = nw.step_host(_lib.ptr_array(ptrs), flags)
+        hout = nw.step_host(_lib.ptr_array(ptrs), flags, with_info=self._native_info)
         nw.torch.cuda.current_stream(nw.device).synchronize()
         self._last_out = hout
         world._obs_valid = False

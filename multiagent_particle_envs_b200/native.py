@@ -61,7 +61,8 @@ class ShapeHandle(object):
 
 class Outputs(object):
     """One slab holding everything a step produces, so that a host caller gets it with a single
-    DMA: obs_0 | obs_1 | ... | rew [A][N] | info [A][INFO][N] | done [A][N] (256-byte aligned parts)."""
+    DMA: obs_0 | obs_1 | ... | rew [A][N] | done [A][N] | info [A][INFO][N] (256-byte aligned parts;
+    mpe_step_host coalesces the adjacent parts into one cudaMemcpyAsync)."""
 
     def __init__(self, nw, pinned_host=False):
         import torch
@@ -72,10 +73,10 @@ class Outputs(object):
             off = _align(off + N * od * 4)
         rew_off = off
         off = _align(off + A * N * 4)
-        info_off = off
-        off = _align(off + A * nw.info_dim * N * 4)
         done_off = off
         off = _align(off + A * N)
+        info_off = off
+        off = _align(off + A * nw.info_dim * N * 4)
         if pinned_host:
             self.slab = torch.empty(off, dtype=torch.uint8, pin_memory=True)
         else:
@@ -164,19 +165,21 @@ class NativeWorld(ShapeHandle):
                                       self.act_c.data_ptr() if self._has_comm else None, self._stream()),
               "mpe_world_step")
 
-    def observe(self, out=None, flags=0):
+    def observe(self, out=None, flags=0, with_info=True):
         out = out or self.out
         pv, lm, comm, goal = self._state_ptrs()
         check(self.lib.mpe_observe(self.handle, pv, lm, comm, goal, out.obs_ptrs, out.rew_ptr, out.done_ptr,
-                                   out.info_ptr, flags, self._stream()), "mpe_observe")
+                                   out.info_ptr if with_info else None, flags, self._stream()), "mpe_observe")
         return out
 
-    def step(self, act_ptrs, out=None, flags=0):
-        """MultiAgentEnv.step fused into one launch; act_ptrs: ctypes array of device pointers"""
+    def step(self, act_ptrs, out=None, flags=0, with_info=False):
+        """MultiAgentEnv.step fused into one launch; act_ptrs: ctypes array of device pointers.
+        benchmark_data (info) is computed and written only when asked for (make_env(benchmark=True))."""
         out = out or self.out
         pv, lm, comm, goal = self._state_ptrs()
         check(self.lib.mpe_step(self.handle, pv, lm, comm, goal, act_ptrs, out.obs_ptrs, out.rew_ptr,
-                                out.done_ptr, out.info_ptr, flags, self._stream()), "mpe_step")
+                                out.done_ptr, out.info_ptr if with_info else None, flags, self._stream()),
+              "mpe_step")
         return out
 
     # ---- host callers (what the reference's callers hold: NumPy arrays) -----------------------
@@ -193,7 +196,7 @@ class NativeWorld(ShapeHandle):
                 host_out=[Outputs(self, pinned_host=True), Outputs(self, pinned_host=True)], flip=0)
         return self._host
 
-    def step_host(self, host_act_ptrs, flags=0, dev_out=None, host_out=None):
+    def step_host(self, host_act_ptrs, flags=0, dev_out=None, host_out=None, with_info=False):
         """H2D actions -> fused step -> D2H outputs, all enqueued on the current stream by
         mpe_step_host; returns the pinned host Outputs (valid after a stream synchronize)."""
         hs = self.host_staging()
@@ -203,8 +206,10 @@ class NativeWorld(ShapeHandle):
             hs["flip"] ^= 1
         pv, lm, comm, goal = self._state_ptrs()
         check(self.lib.mpe_step_host(self.handle, pv, lm, comm, goal, host_act_ptrs, hs["dev_act_ptrs"],
-                                     dev_out.obs_ptrs, dev_out.rew_ptr, dev_out.done_ptr, dev_out.info_ptr,
-                                     host_out.obs_ptrs, host_out.rew_ptr, host_out.done_ptr, host_out.info_ptr,
+                                     dev_out.obs_ptrs, dev_out.rew_ptr, dev_out.done_ptr,
+                                     dev_out.info_ptr if with_info else None,
+                                     host_out.obs_ptrs, host_out.rew_ptr, host_out.done_ptr,
+                                     host_out.info_ptr if with_info else None,
                                      flags, self._stream()), "mpe_step_host")
         return host_out
 

@@ -1,0 +1,253 @@
+"""Parity of the sm_100a kernels (through the C ABI / the reference-shaped Python API) against
+(a) the committed golden fixtures produced by the real reference, and (b) the CPU oracle on seeded
+synthetic worlds.  Tolerance for fp32 vs the fp64 reference: rtol 1e-5, atol 1e-6 per step
+(BASELINE.json north_star); collision counts / done masks bit-exact vs the fp32 oracle evaluated
+on the kernels' own stored state.  Run on the B200 box: pytest -m gpu."""
+import numpy as np
+import pytest
+
+from helpers import CONFIGS, load_golden, make_product_env, random_actions, random_states, split_cols, step_flags
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+RTOL, ATOL = 1e-5, 1e-6
+TAGS = list(CONFIGS)
+
+
+def inject(nw, pv, lm, comm):
+    """oracle layout [n,A,4] / [n,L,2] / [n,A,C] -> the SoA device tensors"""
+    dev = nw.device
+    nw.agent_pv.copy_(torch.as_tensor(pv, dtype=torch.float32, device=dev).permute(1, 0, 2))
+    if nw.n_landmarks:
+        nw.lm_p.copy_(torch.as_tensor(lm, dtype=torch.float32, device=dev).permute(1, 0, 2))
+    C = nw.dim_c
+    for i in range(nw.n_agents):
+        s = nw.speaker_slot(i)
+        if s >= 0 and C:
+            nw.comm[s * C:(s + 1) * C].copy_(torch.as_tensor(comm[:, i, :], dtype=torch.float32, device=dev).t())
+
+
+def extract(nw):
+    pv = nw.agent_pv.permute(1, 0, 2).cpu().numpy()
+    C = nw.dim_c
+    comm = np.zeros((nw.n_env, nw.n_agents, C), np.float32)
+    for i in range(nw.n_agents):
+        s = nw.speaker_slot(i)
+        if s >= 0 and C:
+            comm[:, i, :] = nw.comm[s * C:(s + 1) * C].t().cpu().numpy()
+    return pv, comm
+
+
+def gpu_step(env, act, flags_expected=None):
+    """act: [n, sum_act] -> CUDA step -> numpy (obs [n,sum_obs], rew [n,A], done [n,A], info [n,A,I])"""
+    nw = env.world.native
+    acts = [torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32, device=nw.device)
+            for a in split_cols(act, nw.act_dims)]
+    obs_n, rew_n, done_n, info_n = env.step(acts)
+    torch.cuda.synchronize()
+    obs = np.concatenate([o.cpu().numpy() for o in obs_n], axis=1)
+    rew = torch.stack(rew_n, 1).cpu().numpy()
+    done = torch.stack(done_n, 1).cpu().numpy().astype(np.uint8)
+    out = env._last_out
+    info = out.info.permute(2, 0, 1).cpu().numpy() if out.info is not None else np.zeros((nw.n_env, nw.n_agents, 0))
+    return obs, rew, done, info
+
+
+@pytest.mark.parametrize("tag", TAGS + ["simple_tag_force_discrete"])
+def test_golden_fixtures_single_step(tag):
+    """every recorded reference step, state re-injected each step"""
+    g = load_golden(tag)
+    base = "simple_tag" if tag.startswith("simple_tag") else tag
+    W, T = g["act"].shape[:2]
+    env = make_product_env(base, num_envs=W)
+    env.force_discrete_action = bool(int(g["force_discrete"]))
+    env.reset()
+    nw = env.world.native
+    for t in range(T):
+        inject(nw, g["pv0"] if t == 0 else g["pv"][:, t - 1], g["lm"], g["comm0"] if t == 0 else g["comm"][:, t - 1])
+        obs, rew, done, info = gpu_step(env, g["act"][:, t])
+        pv, comm = extract(nw)
+        np.testing.assert_allclose(pv, g["pv"][:, t], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(comm, g["comm"][:, t], rtol=1e-7, atol=0)
+        np.testing.assert_allclose(obs, g["obs"][:, t], rtol=RTOL, atol=ATOL)
+        assert np.array_equal(done, g["done"][:, t])
+        ok = np.isclose(rew, g["rew"][:, t], rtol=RTOL, atol=5e-6)
+        assert ok.mean() >= 0.99, (t, ok.mean())   # a flipped contact flag changes a reward by >= 1
+        if info.shape[2]:
+            okc = np.isclose(info, g["info"][:, t], rtol=RTOL, atol=5e-6)
+            assert okc.mean() >= 0.99
+
+
+@pytest.mark.parametrize("tag", TAGS)
+def test_golden_fixtures_free_running(tag):
+    """25-step trajectories without re-injection stay close (loose: contacts amplify rounding)"""
+    g = load_golden(tag)
+    W, T = g["act"].shape[:2]
+    env = make_product_env(tag, num_envs=W)
+    env.reset()
+    nw = env.world.native
+    inject(nw, g["pv0"], g["lm"], g["comm0"])
+    for t in range(T):
+        obs, rew, done, info = gpu_step(env, g["act"][:, t])
+    pv, _ = extract(nw)
+    err = np.abs(pv - g["pv"][:, T - 1])
+    assert np.median(err) < 1e-5 and (err < 1e-3).mean() > 0.97
+
+
+@pytest.mark.parametrize("tag,n", [("simple", 4096), ("simple_spread_n3", 8192), ("simple_spread_n6", 4096),
+                                   ("simple_tag", 8192), ("simple_world_comm", 4096)])
+def test_seeded_worlds_vs_oracle(tag, n):
+    from oracle import Oracle
+    from multiagent_particle_envs_b200 import _lib
+    env = make_product_env(tag, num_envs=n)
+    env.reset()
+    nw = env.world.native
+    desc = env.world.descriptor()
+    o64, o32 = Oracle(desc, "f64"), Oracle(desc, "f32")
+    flags = _lib.FLAG_SHARED_REWARD if env.shared_reward else 0
+    rng = np.random.RandomState(1234)
+    pv0, lm, comm0 = random_states(desc, n, rng)
+    pv0, lm, comm0 = pv0.astype(np.float32), lm.astype(np.float32), comm0.astype(np.float32)
+    act = random_actions(nw.act_dims, n, rng).astype(np.float32)
+    inject(nw, pv0, lm, comm0)
+    obs, rew, done, info = gpu_step(env, act)
+    pv, comm = extract(nw)
+    # (1) against the reference arithmetic (fp64) on identical fp32 inputs
+    rpv, rcomm, robs, rrew, rdone, rinfo = o64.step(pv0, lm, comm0, act, flags)
+    np.testing.assert_allclose(pv, rpv, rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(comm, rcomm, rtol=1e-7, atol=0)
+    np.testing.assert_allclose(obs, robs, rtol=RTOL, atol=ATOL)
+    assert np.array_equal(done, rdone)
+    assert np.isclose(rew, rrew, rtol=RTOL, atol=5e-6).mean() > 0.995
+    # (2) flags: the fp32 oracle evaluated on the kernel's OWN stored post-step state must give
+    # bit-identical observations, contact counts and done masks
+    fobs, frew, fdone, finfo = o32.observe(pv, lm, comm, flags)
+    assert np.array_equal(obs, fobs)
+    assert np.array_equal(done, fdone)
+    count_cols = [1, 3] if tag.startswith("simple_spread") else ([0] if info.shape[2] else [])
+    for c in count_cols:                                              # collisions / occupied landmarks
+        assert np.array_equal(info[:, :, c], finfo[:, :, c])
+    np.testing.assert_allclose(rew, frew, rtol=2e-6, atol=2e-6)       # only expf ulps may differ
+    # some worlds really are in contact, otherwise the test proves little
+    if desc.n_agents > 1:
+        assert (np.abs(rpv[:, :, 2:4] - pv0[:, :, 2:4] * 0.75).max(axis=(1, 2)) > 1.0).mean() > 0.05
+
+
+@pytest.mark.parametrize("tag", TAGS)
+def test_fused_step_equals_three_kernel_path(tag):
+    """mpe_step == mpe_set_action -> mpe_world_step -> mpe_observe, bit for bit"""
+    from multiagent_particle_envs_b200 import _lib
+    n = 3000
+    env_a = make_product_env(tag, num_envs=n)
+    env_b = make_product_env(tag, num_envs=n)
+    env_a.reset()
+    env_b.reset()
+    na, nb = env_a.world.native, env_b.world.native
+    desc = env_a.world.descriptor()
+    rng = np.random.RandomState(7)
+    pv0, lm, comm0 = random_states(desc, n, rng)
+    act = random_actions(na.act_dims, n, rng).astype(np.float32)
+    inject(na, pv0, lm, comm0)
+    inject(nb, pv0, lm, comm0)
+    obs, rew, done, info = gpu_step(env_a, act)
+    acts = [torch.as_tensor(np.ascontiguousarray(a), device=nb.device) for a in split_cols(act, nb.act_dims)]
+    flags = _lib.FLAG_SHARED_REWARD if env_b.shared_reward else 0
+    nb.set_action(_lib.ptr_array([t.data_ptr() for t in acts]), flags)
+    env_b.world.step()                      # World.step(), core.py:117
+    out = nb.observe(flags=flags)
+    torch.cuda.synchronize()
+    assert torch.equal(na.agent_pv, nb.agent_pv)
+    assert torch.equal(na.comm, nb.comm)
+    assert np.array_equal(obs, np.concatenate([o.cpu().numpy() for o in out.obs], 1))
+    assert np.array_equal(rew, out.rew.t().cpu().numpy())
+
+
+def test_scalar_api_matches_reference_known_answers():
+    """BASELINE config 1: `simple`, batch 1, the reference's calling convention end to end"""
+    import os
+    from helpers import GOLDEN
+    from make_env import make_env
+    k = dict(np.load(os.path.join(GOLDEN, "kat.npz")))
+    for name in ("simple", "simple_spread", "simple_tag", "simple_world_comm"):
+        env = make_env(name)
+        obs_n = env.reset()
+        assert isinstance(obs_n, list) and obs_n[0].dtype == np.float64 and obs_n[0].ndim == 1
+        world = env.world
+        for i, ag in enumerate(world.agents):           # inject through the reference's own attributes
+            ag.state.p_pos = k[name + "/pv0"][i, 0:2]
+            ag.state.p_vel = k[name + "/pv0"][i, 2:4]
+        for l, lmk in enumerate(world.landmarks):
+            lmk.state.p_pos = k[name + "/lm"][l]
+        acts = split_cols(k[name + "/act"], [5 + (4 if (name == "simple_world_comm" and i == 0) else 0)
+                                             for i in range(env.n)])
+        for _ in range(2):
+            obs_n, rew_n, done_n, info_n = env.step([a.copy() for a in acts])
+        assert len(obs_n) == env.n and all(o.dtype == np.float64 for o in obs_n)
+        assert all(isinstance(d, bool) for d in done_n) and not any(done_n)
+        assert set(info_n) == {"n"} and len(info_n["n"]) == env.n
+        np.testing.assert_allclose(np.concatenate(obs_n), k[name + "/obs"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(np.array(rew_n), k[name + "/rew"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(world.agents[0].state.p_pos, k[name + "/pv"][0, 0:2], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(world.agents[0].state.p_vel, k[name + "/pv"][0, 2:4], rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 127, 129, 1000])
+def test_ragged_batch_sizes(n):
+    """partial warps / partial blocks take the scalar tile path; results equal the big-batch rows"""
+    from oracle import Oracle
+    from multiagent_particle_envs_b200 import _lib
+    tag = "simple_tag"
+    env = make_product_env(tag, num_envs=n)
+    env.reset()
+    nw = env.world.native
+    desc = env.world.descriptor()
+    rng = np.random.RandomState(n)
+    pv0, lm, comm0 = random_states(desc, n, rng)
+    act = random_actions(nw.act_dims, n, rng).astype(np.float32)
+    inject(nw, pv0, lm, comm0)
+    obs, rew, done, info = gpu_step(env, act)
+    pv, _ = extract(nw)
+    rpv, _, robs, rrew, rdone, _ = Oracle(desc, "f64").step(pv0.astype(np.float32), lm.astype(np.float32),
+                                                             comm0, act, 0)
+    np.testing.assert_allclose(pv, rpv, rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(obs, robs, rtol=RTOL, atol=ATOL)
+
+
+def test_unaligned_action_views_are_handled():
+    """non-contiguous / misaligned action tensors are normalised by the wrapper, not rejected"""
+    n = 96
+    env_a = make_product_env("simple_spread_n3", num_envs=n)
+    env_b = make_product_env("simple_spread_n3", num_envs=n)
+    env_a.reset()
+    env_b.reset()
+    env_b.world.native.agent_pv.copy_(env_a.world.native.agent_pv)
+    env_b.world.native.lm_p.copy_(env_a.world.native.lm_p)
+    big = torch.rand(n, 7, device="cuda")
+    oa, ra, _, _ = env_a.step([big[:, 1:6] for _ in range(3)])                  # strided views
+    ob, rb, _, _ = env_b.step([big[:, 1:6].contiguous() for _ in range(3)])
+    for x, y in zip(oa + ra, ob + rb):
+        assert torch.equal(x, y)
+
+
+def test_host_buffers_path_equals_device_path():
+    """NumPy in -> NumPy out through mpe_step_host equals the CUDA-tensor path bit for bit"""
+    n = 2048
+    env_a = make_product_env("simple_world_comm", num_envs=n)
+    env_b = make_product_env("simple_world_comm", num_envs=n)
+    env_a.reset()
+    env_b.reset()
+    env_b.world.native.agent_pv.copy_(env_a.world.native.agent_pv)
+    env_b.world.native.lm_p.copy_(env_a.world.native.lm_p)
+    rng = np.random.RandomState(3)
+    act = random_actions(env_a.world.native.act_dims, n, rng).astype(np.float32)
+    acts = split_cols(act, env_a.world.native.act_dims)
+    for _ in range(3):
+        oa, ra, da, _ = env_a.step([torch.as_tensor(np.ascontiguousarray(a), device="cuda") for a in acts])
+        ob, rb, db, _ = env_b.step([np.ascontiguousarray(a) for a in acts])
+        assert isinstance(ob[0], np.ndarray) and ob[0].shape == (n, 34)
+        for x, y in zip(oa, ob):
+            assert np.array_equal(x.cpu().numpy(), y)
+        for x, y in zip(ra, rb):
+            assert np.array_equal(x.cpu().numpy(), y)
+        assert not any(d.any() for d in db)
