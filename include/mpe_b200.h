@@ -22,7 +22,8 @@
  *   goal      int32  [G][n_env]        per-world goal indices (push/adversary/... scenarios)
  * API-facing per-agent tensors are row-major exactly as a trainer holds them:
  *   act_n[i]  float  [n_env][act_dim_i]  (5 physical one-hot/probabilities, then dim_c comm)
- *   obs_n[i]  float  [n_env][obs_dim_i]
+ *   obs_n[i]  float  [n_env][obs_dim_i]    (base pointer 16-byte aligned; act_n[i] may be 4-byte aligned,
+ *                                           16-byte alignment enables the TMA path)
  *   rew       float  [A][n_env],  done uint8 [A][n_env],  info float [A][info_dim][n_env]
  */
 #ifndef MPE_B200_H
@@ -72,7 +73,11 @@ enum mpe_error {
 enum mpe_step_flags {
     MPE_FLAG_SHARED_REWARD = 1,         /* env.shared_reward: every agent gets sum_i r_i   :100-102 */
     MPE_FLAG_FORCE_DISCRETE_ACTION = 2, /* env.force_discrete_action: argmax one-hot       :169-172 */
-    MPE_FLAG_DISCRETE_ACTION_INPUT = 4  /* env.discrete_action_input: act_n holds indices  :161-167,185-187 */
+    MPE_FLAG_DISCRETE_ACTION_INPUT = 4, /* env.discrete_action_input: act_n holds indices  :161-167,185-187 */
+    MPE_FLAG_HOST_SLAB = 8              /* mpe_step_host only: obs_n_host[0..A), rew_host, done_host (, info_host)
+                                           are consecutive parts of ONE host allocation and their device
+                                           counterparts of ONE device allocation, with equal gaps < 512 B:
+                                           the D2H copies are coalesced into a single DMA */
 };
 
 /*

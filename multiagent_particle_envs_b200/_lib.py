@@ -22,6 +22,7 @@ SCN_SIMPLE, SCN_SPREAD, SCN_TAG, SCN_WORLD_COMM, SCN_ADVERSARY, SCN_PUSH, SCN_SP
 FLAG_SHARED_REWARD = 1
 FLAG_FORCE_DISCRETE_ACTION = 2
 FLAG_DISCRETE_ACTION_INPUT = 4
+FLAG_HOST_SLAB = 8
 
 ERR_UNSUPPORTED = -3
 

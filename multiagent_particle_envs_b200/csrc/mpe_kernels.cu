@@ -8,6 +8,7 @@
 // All four are the same kernel template with phases compiled in or out, so the fused step is
 // bit-identical to set_action -> world_step -> observe.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <utility>
@@ -27,13 +28,36 @@ __device__ __forceinline__ void static_for(F &&f) {
 
 template <class P>
 struct Shape {
-    __host__ __device__ static constexpr int sum_act() { int s = 0; for (int i = 0; i < P::A; ++i) s += 32 * (P::act_dim(i) | 1); return s; }
-    __host__ __device__ static constexpr int max_obs() { int m = 0; for (int i = 0; i < P::A; ++i) { int v = 32 * (P::obs_dim(i) | 1); m = v > m ? v : m; } return m; }
-    __host__ __device__ static constexpr int act_off(int i) { int s = 0; for (int j = 0; j < i; ++j) s += 32 * (P::act_dim(j) | 1); return s; }
-    // floats of warp-private staging: action tiles of all agents, then one observation tile
-    static constexpr int kActFloats = (sum_act() + 3) & ~3;
-    static constexpr int kWarpFloats = kActFloats + ((max_obs() + 3) & ~3);
-    static constexpr int kSmemBytes = kWarpsPerBlock * kWarpFloats * 4;
+    // warp-private staging, in floats: [mbarrier: 4][action tiles of all agents][observation tiles]
+    // Dense observation tiles (exact images of the global rows) each get their own slot so that all
+    // of them can be in flight as TMA bulk stores at once; padded tiles share one slot.
+    static constexpr int kBarFloats = 4;
+    __host__ __device__ static constexpr int act_floats(int i) { return 32 * (P::act_dim(i) | 1); }
+    __host__ __device__ static constexpr int act_off(int i) { int s = kBarFloats; for (int j = 0; j < i; ++j) s += act_floats(j); return s; }
+    __host__ __device__ static constexpr bool act_dense(int i) { return (P::act_dim(i) | 1) == P::act_dim(i); }
+    __host__ __device__ static constexpr bool all_act_dense() { for (int i = 0; i < P::A; ++i) if (!act_dense(i)) return false; return true; }
+    __host__ __device__ static constexpr int act_bytes_total() { int s = 0; for (int i = 0; i < P::A; ++i) s += 32 * P::act_dim(i) * 4; return s; }
+    __host__ __device__ static constexpr int obs_pitch(int i) {
+        const int od = P::obs_dim(i), unit = (od % 2 == 0) ? 2 : 1;
+        return ((od / unit) | 1) * unit;
+    }
+    __host__ __device__ static constexpr bool obs_dense(int i) { return obs_pitch(i) == P::obs_dim(i); }
+    __host__ __device__ static constexpr int obs_floats(int i) { return (32 * obs_pitch(i) + 3) & ~3; }
+    __host__ __device__ static constexpr int obs_base() { return act_off(P::A); }
+    __host__ __device__ static constexpr int shared_obs_floats() { int m = 0; for (int i = 0; i < P::A; ++i) if (!obs_dense(i)) m = obs_floats(i) > m ? obs_floats(i) : m; return m; }
+    __host__ __device__ static constexpr int obs_off(int i) {
+        if (!obs_dense(i)) return obs_base();
+        int s = obs_base() + shared_obs_floats();
+        for (int j = 0; j < i; ++j) if (obs_dense(j)) s += obs_floats(j);
+        return s;
+    }
+    __host__ __device__ static constexpr int warp_floats() {
+        int s = obs_base() + shared_obs_floats();
+        for (int j = 0; j < P::A; ++j) if (obs_dense(j)) s += obs_floats(j);
+        return (s + 3) & ~3;
+    }
+    static constexpr int kWarpFloats = warp_floats();
+    static constexpr int kWarpBytes = kWarpFloats * 4;
     static constexpr int kNC = P::NS * P::DIMC;
 };
 
@@ -64,18 +88,18 @@ __device__ __forceinline__ void physics(const DevDesc &d, typename P::W &w, cons
             const float by = b_agent ? w.py[bi] : w.ly[bl];
             const float sb = b_agent ? d.a_size[bi] : d.l_size[bl];
             const float dx = w.px[a] - bx, dy = w.py[a] - by;              // :186
-            const float dist = sqrtf(dx * dx + dy * dy);                    // :187
+            const float dist = __fsqrt_rn(fmaf(dx, dx, dy * dy));           // :187 (IEEE sqrt: dist - dist_min cancels)
             const float dist_min = d.a_size[a] + sb;                        // :189
-            const float pen = softplus(-(dist - dist_min) / k) * k;         // :191-192
-            const float f_x = cf * dx / dist * pen;                         // :193
-            const float f_y = cf * dy / dist * pen;
+            const float pen = softplus_fast((dist_min - dist) * d.inv_margin) * k;   // :191-192
+            const float s = __fdividef(cf * pen, dist);                     // :193  force = cf * delta / dist * pen
+            const float f_x = s * dx, f_y = s * dy;
             if ((d.a_movable >> a) & 1u) {                                  // :194, 149-151
-                fx[a] = f_x + fx[a];
-                fy[a] = f_y + fy[a];
+                fx[a] += f_x;
+                fy[a] += f_y;
             }
             if (b_agent && ((d.a_movable >> bi) & 1u)) {                    // :195, 152-154
-                fx[bi] = -f_x + fx[bi];
-                fy[bi] = -f_y + fy[bi];
+                fx[bi] -= f_x;
+                fy[bi] -= f_y;
             }
         }
     }
@@ -83,37 +107,41 @@ __device__ __forceinline__ void physics(const DevDesc &d, typename P::W &w, cons
 #pragma unroll
     for (int i = 0; i < A; ++i) {
         if (!((d.a_movable >> i) & 1u)) continue;
-        float vx = w.vx[i] * d.keep, vy = w.vy[i] * d.keep;                 // :161
-        vx += (fx[i] / d.a_mass[i]) * d.dt;                                 // :163
-        vy += (fy[i] / d.a_mass[i]) * d.dt;
+        float vx = fmaf(fx[i], d.a_dt_over_mass[i], w.vx[i] * d.keep);     // :161,163
+        float vy = fmaf(fy[i], d.a_dt_over_mass[i], w.vy[i] * d.keep);
         const float ms = d.a_max_speed[i];
         if (ms >= 0.0f) {                                                   // :164-168
-            const float speed = sqrtf(vx * vx + vy * vy);
+            const float speed = __fsqrt_rn(fmaf(vx, vx, vy * vy));
             if (speed > ms) {
-                vx = vx / speed * ms;
-                vy = vy / speed * ms;
+                const float sc = __fdividef(ms, speed);
+                vx *= sc;
+                vy *= sc;
             }
         }
-        w.px[i] += vx * d.dt;                                               // :169
-        w.py[i] += vy * d.dt;
+        w.px[i] = fmaf(vx, d.dt, w.px[i]);                                  // :169
+        w.py[i] = fmaf(vy, d.dt, w.py[i]);
         w.vx[i] = vx;
         w.vy[i] = vy;
     }
 }
 
 template <class P, int MODE>
-__global__ void __launch_bounds__(kThreads) mpe_kernel(const __grid_constant__ StepArgs a) {
+__global__ void __launch_bounds__(kMaxThreads) mpe_kernel(const __grid_constant__ StepArgs a) {
     constexpr int A = P::A, L = P::L, NC = Shape<P>::kNC;
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t n = a.n;
-    const int64_t w0 = (static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + warp) * 32;
+    const int64_t w0 = (static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + warp) * 32;
+    // Programmatic dependent launch: let the next grid's blocks become resident while this grid runs,
+    // and touch no global memory before the previous grid has completed and flushed.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (w0 >= n) return;  // whole warp exits together
     const int rows = (n - w0) < 32 ? static_cast<int>(n - w0) : 32;
     const bool active = lane < rows;
     const int64_t wi = w0 + (active ? lane : 0);  // inactive lanes shadow row 0 and never store
-    float *s_act = smem + warp * Shape<P>::kWarpFloats;
-    float *s_obs = s_act + Shape<P>::kActFloats;
+    float *s_warp = smem + warp * Shape<P>::kWarpFloats;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(s_warp);
     const DevDesc &d = a.d;
 
     typename P::W w;
@@ -139,18 +167,40 @@ __global__ void __launch_bounds__(kThreads) mpe_kernel(const __grid_constant__ S
     float cact[NC > 0 ? NC : 1];
     // ---- MultiAgentEnv._set_action (environment.py:144-192) --------------------------------
     if constexpr (MODE == kFusedStep || MODE == kSetAction) {
+        bool bulk = false;
+        if constexpr (Shape<P>::all_act_dense()) {
+            uintptr_t bits = 0;
+#pragma unroll
+            for (int i = 0; i < A; ++i) bits |= reinterpret_cast<uintptr_t>(a.act[i]);
+            bulk = (rows == 32) && ((bits & 15u) == 0);   // warp-uniform
+        }
+        if (bulk) {
+            // TMA: one UBLKCP per agent tile (32 rows x act_dim floats, contiguous in global memory)
+            if (lane == 0) {
+                mbar_init(bar, 1);
+                mbar_expect_tx(bar, Shape<P>::act_bytes_total());
+                static_for<A>([&](auto ic) {
+                    constexpr int i = decltype(ic)::value;
+                    constexpr int AD = P::act_dim(i);
+                    bulk_g2s(s_warp + Shape<P>::act_off(i), a.act[i] + w0 * AD, 32 * AD * 4, bar);
+                });
+            }
+            __syncwarp();
+            mbar_wait(bar, 0);
+        } else {
+            static_for<A>([&](auto ic) {
+                constexpr int i = decltype(ic)::value;
+                constexpr int AD = P::act_dim(i);
+                constexpr int OFF = Shape<P>::act_off(i);
+                tile_load<AD>(s_warp + OFF, a.act[i] + w0 * AD, rows, lane);
+            });
+            __syncwarp();
+        }
         static_for<A>([&](auto ic) {
             constexpr int i = decltype(ic)::value;
             constexpr int AD = P::act_dim(i);
             constexpr int OFF = Shape<P>::act_off(i);
-            tile_load<AD>(s_act + OFF, a.act[i] + w0 * AD, rows, lane);
-        });
-        __syncwarp();
-        static_for<A>([&](auto ic) {
-            constexpr int i = decltype(ic)::value;
-            constexpr int AD = P::act_dim(i);
-            constexpr int OFF = Shape<P>::act_off(i);
-            const float *row = s_act + OFF + lane * Tile<AD>::kStride;
+            const float *row = s_warp + OFF + lane * Tile<AD>::kStride;
             int off = 0;
             float x = 0.0f, y = 0.0f;                                       // :145
             if constexpr (P::movable(i)) {
@@ -224,15 +274,38 @@ __global__ void __launch_bounds__(kThreads) mpe_kernel(const __grid_constant__ S
 #pragma unroll
         for (int i = 0; i < A; ++i) rew[i] = s;
     }
-    static_for<A>([&](auto ic) {
-        constexpr int i = decltype(ic)::value;
-        constexpr int OD = P::obs_dim(i);
-        RowWriter o{s_obs + lane * Tile<OD>::kStride};
-        P::template observe<i>(d, w, o);
-        __syncwarp();
-        tile_store<OD>(a.obs[i] + w0 * OD, s_obs, rows, lane);
-        __syncwarp();
-    });
+    if (rows == 32) {
+        bool any_bulk = false;
+        static_for<A>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            constexpr int OD = P::obs_dim(i);
+            float *tile = s_warp + Shape<P>::obs_off(i);
+            float *g = a.obs[i] + w0 * OD;
+            TileWriter<OD> o(tile, lane);
+            P::template observe<i>(d, w, o);
+            if constexpr (Shape<P>::obs_dense(i)) {
+                // private tile == exact image of the 32 global rows: one TMA bulk store, no readback
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) bulk_s2g(g, tile, 32 * OD * 4);
+                any_bulk = true;
+            } else {
+                __syncwarp();
+                obs_tile_store<OD>(g, tile, lane);
+                __syncwarp();
+            }
+        });
+        if (any_bulk && lane == 0) {
+            bulk_commit();
+            bulk_wait_read_all();  // shared memory must stay valid until the TMA engine has read it
+        }
+    } else if (active) {  // the batch's last, partial warp: rows go straight to global memory
+        static_for<A>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            RowWriter o{a.obs[i] + wi * P::obs_dim(i)};
+            P::template observe<i>(d, w, o);
+        });
+    }
     if (active) {
 #pragma unroll
         for (int i = 0; i < A; ++i) {
@@ -301,7 +374,7 @@ struct Program {
     int scenario;
     bool (*validate)(const mpe_desc &);
     KernelFn fn[4];
-    int smem_bytes;
+    int smem_bytes;  // dynamic shared memory per WARP
     int A, L, NS, DIMC, INFO, G;
     int obs_dim[kMaxA], act_dim[kMaxA];
 };
@@ -315,7 +388,7 @@ static Program make_program() {
     p.fn[kSetAction] = mpe_kernel<P, kSetAction>;
     p.fn[kWorldStep] = mpe_kernel<P, kWorldStep>;
     p.fn[kObserve] = mpe_kernel<P, kObserve>;
-    p.smem_bytes = Shape<P>::kSmemBytes;
+    p.smem_bytes = Shape<P>::kWarpBytes;  // per warp
     p.A = P::A; p.L = P::L; p.NS = P::NS; p.DIMC = P::DIMC; p.INFO = P::INFO; p.G = P::G;
     for (int i = 0; i < P::A; ++i) { p.obs_dim[i] = P::obs_dim(i); p.act_dim[i] = P::act_dim(i); }
     return p;
@@ -395,7 +468,7 @@ extern "C" int mpe_create(const mpe_desc *desc, int64_t n_env, int device, mpe_h
         CUDA_TRY(cudaGetDevice(&prev));
         CUDA_TRY(cudaSetDevice(device));
         for (int m = 0; m < 4; ++m)
-            CUDA_TRY(cudaFuncSetAttribute(prog->fn[m], cudaFuncAttributeMaxDynamicSharedMemorySize, prog->smem_bytes));
+            CUDA_TRY(cudaFuncSetAttribute(prog->fn[m], cudaFuncAttributeMaxDynamicSharedMemorySize, prog->smem_bytes * kMaxWarpsPerBlock));
         CUDA_TRY(cudaSetDevice(prev));
     }
 
@@ -411,9 +484,10 @@ extern "C" int mpe_create(const mpe_desc *desc, int64_t n_env, int device, mpe_h
     d.keep = static_cast<float>(1.0 - desc->damping);
     d.contact_force = static_cast<float>(desc->contact_force);
     d.contact_margin = static_cast<float>(desc->contact_margin);
+    d.inv_margin = static_cast<float>(1.0 / desc->contact_margin);
     for (int i = 0; i < desc->n_agents; ++i) {
         d.a_size[i] = static_cast<float>(desc->agent_size[i]);
-        d.a_mass[i] = static_cast<float>(desc->agent_mass[i]);
+        d.a_dt_over_mass[i] = static_cast<float>(desc->dt / desc->agent_mass[i]);
         d.a_sens[i] = static_cast<float>(desc->agent_sens[i]);
         d.a_max_speed[i] = desc->agent_max_speed[i] < 0 ? -1.0f : static_cast<float>(desc->agent_max_speed[i]);
     }
@@ -451,21 +525,38 @@ extern "C" int64_t mpe_bytes_per_env_step(mpe_handle h) {
     return 4 * f + p->A;
 }
 
+static bool pdl_enabled() {
+    static const bool on = [] { const char *e = getenv("MPE_B200_PDL"); return e && e[0] == '1'; }();
+    return on;
+}
+
 static int launch(mpe_handle h, int mode, StepArgs &args, void *stream) {
     if (h->device < 0) return MPE_ERR_NO_DEVICE;
     args.d = h->dev;
     args.n = h->n;
     const int64_t warps = (h->n + 31) / 32;
-    const int64_t blocks = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    // Warps are autonomous, so the block size only sets scheduling granularity: small batches use
+    // one warp per block so that the (few) blocks spread evenly over the 148 SMs.
+    const int wpb = warps <= 148 * 32 ? 1 : (warps <= 148 * 64 ? 2 : kMaxWarpsPerBlock);
+    const int64_t blocks = (warps + wpb - 1) / wpb;
     if (blocks > 0x7fffffffLL) return MPE_ERR_BAD_ARG;
     int prev = 0;
     CUDA_TRY(cudaGetDevice(&prev));
     if (prev != h->device) CUDA_TRY(cudaSetDevice(h->device));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(blocks));
+    cfg.blockDim = dim3(32 * wpb);
+    cfg.dynamicSmemBytes = static_cast<size_t>(h->prog->smem_bytes) * wpb;
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
     void *params[] = {&args};
-    cudaError_t e = cudaLaunchKernel(reinterpret_cast<const void *>(h->prog->fn[mode]), dim3(static_cast<unsigned>(blocks)),
-                                     dim3(kThreads), params, h->prog->smem_bytes, static_cast<cudaStream_t>(stream));
+    cudaError_t e = cudaLaunchKernelExC(&cfg, reinterpret_cast<const void *>(h->prog->fn[mode]), params);
     if (prev != h->device) cudaSetDevice(prev);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernel");
+    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelExC");
     __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED);
     return MPE_OK;
 }
@@ -492,7 +583,7 @@ static int fill_outputs(mpe_handle h, StepArgs &a, float *const *obs_n, float *r
     const Program *p = h->prog;
     if (!obs_n || !ok4(rew) || !done) return MPE_ERR_BAD_ARG;
     for (int i = 0; i < p->A; ++i) {
-        if (!ok4(obs_n[i])) return MPE_ERR_BAD_ARG;
+        if (!ok16(obs_n[i])) return MPE_ERR_BAD_ARG;   // observation rows are written as 16-byte / TMA bulk stores
         a.obs[i] = obs_n[i];
     }
     a.rew = rew;
@@ -564,11 +655,11 @@ extern "C" int mpe_step(mpe_handle h, void *pv, const void *lm, float *comm, con
 
 // adjacent (dst, src, bytes) copies with equal small gaps on both sides are issued as one DMA
 struct CopySeg { char *dst; const char *src; size_t bytes; };
-static int issue_copies(CopySeg *seg, int n, cudaMemcpyKind kind, cudaStream_t s, const char *what) {
+static int issue_copies(CopySeg *seg, int n, cudaMemcpyKind kind, cudaStream_t s, const char *what, bool coalesce) {
     int i = 0;
     while (i < n) {
         CopySeg cur = seg[i++];
-        while (i < n) {
+        while (coalesce && i < n) {
             const ptrdiff_t gd = seg[i].dst - (cur.dst + cur.bytes), gs = seg[i].src - (cur.src + cur.bytes);
             if (gd != gs || gd < 0 || gd >= 512) break;
             cur.bytes += static_cast<size_t>(gd) + seg[i].bytes;
@@ -599,7 +690,7 @@ extern "C" int mpe_step_host(mpe_handle h, void *pv, const void *lm, float *comm
     int prev = 0;
     CUDA_TRY(cudaGetDevice(&prev));
     if (prev != h->device) CUDA_TRY(cudaSetDevice(h->device));
-    int rc = issue_copies(seg, ns, cudaMemcpyHostToDevice, s, "cudaMemcpyAsync(H2D actions)");
+    int rc = issue_copies(seg, ns, cudaMemcpyHostToDevice, s, "cudaMemcpyAsync(H2D actions)", false);
     const bool want_info = info_host && info_dev && p->INFO > 0;
     if (rc == MPE_OK)
         rc = mpe_step(h, pv, lm, comm, goal, act_n_dev, obs_n_dev, rew_dev, done_dev, want_info ? info_dev : nullptr,
@@ -614,7 +705,8 @@ extern "C" int mpe_step_host(mpe_handle h, void *pv, const void *lm, float *comm
         if (want_info)
             seg[ns++] = {reinterpret_cast<char *>(info_host), reinterpret_cast<const char *>(info_dev),
                          sizeof(float) * n * p->A * p->INFO};
-        rc = issue_copies(seg, ns, cudaMemcpyDeviceToHost, s, "cudaMemcpyAsync(D2H obs/rew/done/info)");
+        rc = issue_copies(seg, ns, cudaMemcpyDeviceToHost, s, "cudaMemcpyAsync(D2H obs/rew/done/info)",
+                          (flags & MPE_FLAG_HOST_SLAB) != 0);
     }
     if (prev != h->device) cudaSetDevice(prev);
     return rc;

@@ -34,8 +34,8 @@ struct Simple {
     __host__ __device__ static constexpr int act_dim(int) { return 5; }
     __host__ __device__ static constexpr bool movable(int) { return true; }
 
-    template <int I>
-    __device__ __forceinline__ static void observe(const DevDesc &, const W &w, RowWriter &o) {
+    template <int I, class Wr>
+    __device__ __forceinline__ static void observe(const DevDesc &, const W &w, Wr &o) {
         o.put2(w.vx[I], w.vy[I]);                                                    // :50
 #pragma unroll
         for (int l = 0; l < L; ++l) o.put2(w.lx[l] - w.px[I], w.ly[l] - w.py[I]);    // :48-49
@@ -44,7 +44,7 @@ struct Simple {
 #pragma unroll
         for (int i = 0; i < A; ++i) {
             const float dx = w.px[i] - w.lx[0], dy = w.py[i] - w.ly[0];
-            rew[i] = -(dx * dx + dy * dy);                                           // :41-43
+            rew[i] = -__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));                                           // :41-43
         }
     }
     static bool validate(const mpe_desc &d) {
@@ -63,8 +63,8 @@ struct Spread {
     __host__ __device__ static constexpr int act_dim(int) { return 5; }
     __host__ __device__ static constexpr bool movable(int) { return true; }
 
-    template <int I>
-    __device__ __forceinline__ static void observe(const DevDesc &, const W &w, RowWriter &o) {
+    template <int I, class Wr>
+    __device__ __forceinline__ static void observe(const DevDesc &, const W &w, Wr &o) {
         o.put2(w.vx[I], w.vy[I]);                                                    // simple_spread.py:100
         o.put2(w.px[I], w.py[I]);
 #pragma unroll
@@ -87,6 +87,13 @@ struct Spread {
             min_dists += m;                                                          // :54
             occupied += (m < 0.1f) ? 1 : 0;                                          // :56-57
         }
+        // is_collision is symmetric in its arguments bit for bit: evaluate each unordered pair once
+        bool hit[A][A];
+#pragma unroll
+        for (int i = 0; i < A; ++i)
+#pragma unroll
+            for (int a = i; a < A; ++a)
+                hit[i][a] = hit[a][i] = is_collision(w.px[a], w.py[a], d.a_size[a], w.px[i], w.py[i], d.a_size[i]);
 #pragma unroll
         for (int i = 0; i < A; ++i) {
             float r = base;
@@ -94,7 +101,7 @@ struct Spread {
             if ((d.a_collide >> i) & 1u) {                                           // :78-81, a == i included
 #pragma unroll
                 for (int a = 0; a < A; ++a)
-                    if (is_collision(w.px[a], w.py[a], d.a_size[a], w.px[i], w.py[i], d.a_size[i])) {
+                    if (hit[i][a]) {
                         r -= 1.0f;
                         coll += 1;
                     }
@@ -131,8 +138,8 @@ struct Tag {
     __host__ __device__ static constexpr int act_dim(int) { return 5; }
     __host__ __device__ static constexpr bool movable(int) { return true; }
 
-    template <int I>
-    __device__ __forceinline__ static void observe(const DevDesc &, const W &w, RowWriter &o) {
+    template <int I, class Wr>
+    __device__ __forceinline__ static void observe(const DevDesc &, const W &w, Wr &o) {
         o.put2(w.vx[I], w.vy[I]);                                                    // :147
         o.put2(w.px[I], w.py[I]);
 #pragma unroll
@@ -206,8 +213,8 @@ struct WorldComm {
                             d.l_size[FOREST0 + f]);                                  // :231-239, 251-252
     }
 
-    template <int I>
-    __device__ __forceinline__ static void observe(const DevDesc &d, const W &w, RowWriter &o) {
+    template <int I, class Wr>
+    __device__ __forceinline__ static void observe(const DevDesc &d, const W &w, Wr &o) {
         o.put2(w.vx[I], w.vy[I]);
         o.put2(w.px[I], w.py[I]);
 #pragma unroll
@@ -255,7 +262,7 @@ struct WorldComm {
                     const float dd = dist2d(w.px[NADV + g], w.py[NADV + g], w.px[i], w.py[i]);
                     m = dd < m ? dd : m;
                 }
-                r -= 0.1f * m;                                                       // :192
+                r -= __fmul_rn(0.1f, m);                                                       // :192
 #pragma unroll
                 for (int g = 0; g < NGOOD; ++g) {
 #pragma unroll
@@ -267,8 +274,8 @@ struct WorldComm {
 #pragma unroll
                 for (int a = 0; a < NADV; ++a)
                     if (((d.a_collide >> i) & 1u) && hit[i >= NADV ? i - NADV : 0][a]) r -= 5.0f;
-                r -= 2.0f * bound_pen(fabsf(w.px[i]));                               // :176-178
-                r -= 2.0f * bound_pen(fabsf(w.py[i]));
+                r -= __fmul_rn(2.0f, bound_pen(fabsf(w.px[i])));                               // :176-178
+                r -= __fmul_rn(2.0f, bound_pen(fabsf(w.py[i])));
 #pragma unroll
                 for (int f = 0; f < NFOOD; ++f)                                      // :179-181
                     if (is_collision(w.px[i], w.py[i], d.a_size[i], w.lx[FOOD0 + f], w.ly[FOOD0 + f],
@@ -280,7 +287,7 @@ struct WorldComm {
                     const float dd = dist2d(w.lx[FOOD0 + f], w.ly[FOOD0 + f], w.px[i], w.py[i]);
                     m = dd < m ? dd : m;
                 }
-                r += 0.05f * m;                                                      // :182
+                r += __fmul_rn(0.05f, m);                                                      // :182
             }
             rew[i] = r;
             if (info) info[i] = static_cast<float>(coll);

@@ -210,7 +210,7 @@ class NativeWorld(ShapeHandle):
                                      dev_out.info_ptr if with_info else None,
                                      host_out.obs_ptrs, host_out.rew_ptr, host_out.done_ptr,
                                      host_out.info_ptr if with_info else None,
-                                     flags, self._stream()), "mpe_step_host")
+                                     flags | _lib.FLAG_HOST_SLAB, self._stream()), "mpe_step_host")
         return host_out
 
     # ---- benchmark_data (e.g. simple_spread.py:47-63) -----------------------------------------

@@ -128,7 +128,7 @@ def test_reset_distribution_mask_and_sharding():
     assert abs(float(lm.var()) - 0.27) < 5e-3
     # no two entities share a draw
     flat = torch.cat([pos.reshape(-1, n, 2), lm], 0)[:, :1000].reshape(-1)
-    assert flat.unique().numel() == flat.numel()
+    assert flat.unique().numel() > 0.995 * flat.numel()      # 24-bit uniforms: a few birthday collisions
     # masked reset touches only the masked worlds, and successive resets differ
     before = nw.agent_pv.clone()
     mask = torch.zeros(n, dtype=torch.bool, device="cuda")
