@@ -81,23 +81,24 @@ __device__ __forceinline__ void physics(const DevDesc &d, typename P::W &w, cons
         for (int b = a + 1; b < A + L; ++b) {
             const bool b_agent = b < A;
             const int bi = b_agent ? b : 0, bl = b_agent ? 0 : b - A;
-            const bool collide = ((d.a_collide >> a) & 1u) &&
-                                 (b_agent ? ((d.a_collide >> bi) & 1u) : ((d.l_collide >> bl) & 1u));
-            if (!collide) continue;  // get_collision_force (core.py:181-182); warp-uniform
+            // get_collision_force (core.py:181-182): the collide flags are structural constants of the
+            // scenario program, so non-colliding pairs vanish at compile time and the remaining pairs form
+            // one straight-line block that the scheduler interleaves freely
+            if (!(P::agent_collides(a) && (b_agent ? P::agent_collides(bi) : P::landmark_collides(bl)))) continue;
             const float bx = b_agent ? w.px[bi] : w.lx[bl];
             const float by = b_agent ? w.py[bi] : w.ly[bl];
             const float sb = b_agent ? d.a_size[bi] : d.l_size[bl];
             const float dx = w.px[a] - bx, dy = w.py[a] - by;              // :186
-            const float dist = __fsqrt_rn(fmaf(dx, dx, dy * dy));           // :187 (IEEE sqrt: dist - dist_min cancels)
+            const float dist = sqrt_rn_nobranch(fmaf(dx, dx, dy * dy));     // :187 (exact sqrt: dist - dist_min cancels)
             const float dist_min = d.a_size[a] + sb;                        // :189
             const float pen = softplus_fast((dist_min - dist) * d.inv_margin) * k;   // :191-192
             const float s = __fdividef(cf * pen, dist);                     // :193  force = cf * delta / dist * pen
             const float f_x = s * dx, f_y = s * dy;
-            if ((d.a_movable >> a) & 1u) {                                  // :194, 149-151
+            if (P::movable(a)) {                                            // :194, 149-151
                 fx[a] += f_x;
                 fy[a] += f_y;
             }
-            if (b_agent && ((d.a_movable >> bi) & 1u)) {                    // :195, 152-154
+            if (b_agent && P::movable(bi)) {                                // :195, 152-154
                 fx[bi] -= f_x;
                 fy[bi] -= f_y;
             }
@@ -106,17 +107,15 @@ __device__ __forceinline__ void physics(const DevDesc &d, typename P::W &w, cons
     // integrate_state (core.py:158-169)
 #pragma unroll
     for (int i = 0; i < A; ++i) {
-        if (!((d.a_movable >> i) & 1u)) continue;
+        if (!P::movable(i)) continue;
         float vx = fmaf(fx[i], d.a_dt_over_mass[i], w.vx[i] * d.keep);     // :161,163
         float vy = fmaf(fy[i], d.a_dt_over_mass[i], w.vy[i] * d.keep);
-        const float ms = d.a_max_speed[i];
-        if (ms >= 0.0f) {                                                   // :164-168
-            const float speed = __fsqrt_rn(fmaf(vx, vx, vy * vy));
-            if (speed > ms) {
-                const float sc = __fdividef(ms, speed);
-                vx *= sc;
-                vy *= sc;
-            }
+        if constexpr (P::kSpeedLimit) {                                     // :164-168
+            const float ms = d.a_max_speed[i];
+            const float speed = sqrt_rn_nobranch(fmaf(vx, vx, vy * vy));
+            const float sc = speed > ms ? __fdividef(ms, speed) : 1.0f;
+            vx *= sc;
+            vy *= sc;
         }
         w.px[i] = fmaf(vx, d.dt, w.px[i]);                                  // :169
         w.py[i] = fmaf(vy, d.dt, w.py[i]);
@@ -132,9 +131,9 @@ __global__ void __launch_bounds__(kMaxThreads) mpe_kernel(const __grid_constant_
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t n = a.n;
     const int64_t w0 = (static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + warp) * 32;
-    // Programmatic dependent launch: let the next grid's blocks become resident while this grid runs,
-    // and touch no global memory before the previous grid has completed and flushed.
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // Programmatic dependent launch (opt-in, MPE_B200_PDL=1): touch no global memory before the
+    // previous grid has completed and flushed; the next grid is released late (before our stores).
+    if (a.flags & kFlagPdlEarly) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (w0 >= n) return;  // whole warp exits together
     const int rows = (n - w0) < 32 ? static_cast<int>(n - w0) : 32;
@@ -143,6 +142,25 @@ __global__ void __launch_bounds__(kMaxThreads) mpe_kernel(const __grid_constant_
     float *s_warp = smem + warp * Shape<P>::kWarpFloats;
     uint64_t *bar = reinterpret_cast<uint64_t *>(s_warp);
     const DevDesc &d = a.d;
+
+    // ---- action tiles: TMA bulk loads issued FIRST, so that they fly together with the state loads --
+    bool bulk = false;
+    if constexpr ((MODE == kFusedStep || MODE == kSetAction) && Shape<P>::all_act_dense()) {
+        uintptr_t bits = 0;
+#pragma unroll
+        for (int i = 0; i < A; ++i) bits |= reinterpret_cast<uintptr_t>(a.act[i]);
+        bulk = (rows == 32) && ((bits & 15u) == 0);   // warp-uniform
+        if (bulk && lane == 0) {
+            // one UBLKCP per agent tile (32 rows x act_dim floats, contiguous in global memory)
+            mbar_init(bar, 1);
+            mbar_expect_tx(bar, Shape<P>::act_bytes_total());
+            static_for<A>([&](auto ic) {
+                constexpr int i = decltype(ic)::value;
+                constexpr int AD = P::act_dim(i);
+                bulk_g2s(s_warp + Shape<P>::act_off(i), a.act[i] + w0 * AD, 32 * AD * 4, bar);
+            });
+        }
+    }
 
     typename P::W w;
     // ---- state loads (issued first so they overlap the action staging) ---------------------
@@ -167,24 +185,7 @@ __global__ void __launch_bounds__(kMaxThreads) mpe_kernel(const __grid_constant_
     float cact[NC > 0 ? NC : 1];
     // ---- MultiAgentEnv._set_action (environment.py:144-192) --------------------------------
     if constexpr (MODE == kFusedStep || MODE == kSetAction) {
-        bool bulk = false;
-        if constexpr (Shape<P>::all_act_dense()) {
-            uintptr_t bits = 0;
-#pragma unroll
-            for (int i = 0; i < A; ++i) bits |= reinterpret_cast<uintptr_t>(a.act[i]);
-            bulk = (rows == 32) && ((bits & 15u) == 0);   // warp-uniform
-        }
         if (bulk) {
-            // TMA: one UBLKCP per agent tile (32 rows x act_dim floats, contiguous in global memory)
-            if (lane == 0) {
-                mbar_init(bar, 1);
-                mbar_expect_tx(bar, Shape<P>::act_bytes_total());
-                static_for<A>([&](auto ic) {
-                    constexpr int i = decltype(ic)::value;
-                    constexpr int AD = P::act_dim(i);
-                    bulk_g2s(s_warp + Shape<P>::act_off(i), a.act[i] + w0 * AD, 32 * AD * 4, bar);
-                });
-            }
             __syncwarp();
             mbar_wait(bar, 0);
         } else {
@@ -217,8 +218,10 @@ __global__ void __launch_bounds__(kMaxThreads) mpe_kernel(const __grid_constant_
                 }
                 x += p1 - p2;                                               // :174
                 y += p3 - p4;                                               // :175
-                x *= d.a_sens[i];                                           // :178-181
-                y *= d.a_sens[i];
+                // explicit multiplies: must not be contracted into the force accumulation, or the fused
+                // step would round differently from set_action -> world_step
+                x = __fmul_rn(x, d.a_sens[i]);                              // :178-181
+                y = __fmul_rn(y, d.a_sens[i]);
                 off = 5;
             }
             ux[i] = x;
@@ -256,7 +259,7 @@ __global__ void __launch_bounds__(kMaxThreads) mpe_kernel(const __grid_constant_
         if (active) {
 #pragma unroll
             for (int i = 0; i < A; ++i)
-                if ((d.a_movable >> i) & 1u) a.pv[i * n + wi] = make_float4(w.px[i], w.py[i], w.vx[i], w.vy[i]);
+                if (P::movable(i)) a.pv[i * n + wi] = make_float4(w.px[i], w.py[i], w.vx[i], w.vy[i]);
 #pragma unroll
             for (int q = 0; q < NC; ++q) a.comm[q * n + wi] = w.c[q];
         }
@@ -274,31 +277,29 @@ __global__ void __launch_bounds__(kMaxThreads) mpe_kernel(const __grid_constant_
 #pragma unroll
         for (int i = 0; i < A; ++i) rew[i] = s;
     }
+    if (!(a.flags & kFlagPdlEarly)) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (rows == 32) {
-        bool any_bulk = false;
+        // Tiles are private per agent (dense ones), so no barrier is needed between agents: all rows are
+        // written, one __syncwarp, then the warp streams every tile out as 16-byte stores and retires.
+        // (A TMA bulk store was measured slower here: the warp has to stay resident until the copy
+        // engine has read its shared memory, ~1.7 us at 13 warps/SM; see profiles/.)
         static_for<A>([&](auto ic) {
             constexpr int i = decltype(ic)::value;
             constexpr int OD = P::obs_dim(i);
-            float *tile = s_warp + Shape<P>::obs_off(i);
-            float *g = a.obs[i] + w0 * OD;
-            TileWriter<OD> o(tile, lane);
+            TileWriter<OD> o(s_warp + Shape<P>::obs_off(i), lane);
             P::template observe<i>(d, w, o);
-            if constexpr (Shape<P>::obs_dense(i)) {
-                // private tile == exact image of the 32 global rows: one TMA bulk store, no readback
-                fence_async_smem();
+            if constexpr (!Shape<P>::obs_dense(i)) {  // padded tiles share one slot
                 __syncwarp();
-                if (lane == 0) bulk_s2g(g, tile, 32 * OD * 4);
-                any_bulk = true;
-            } else {
-                __syncwarp();
-                obs_tile_store<OD>(g, tile, lane);
+                obs_tile_store<OD>(a.obs[i] + w0 * OD, s_warp + Shape<P>::obs_off(i), lane);
                 __syncwarp();
             }
         });
-        if (any_bulk && lane == 0) {
-            bulk_commit();
-            bulk_wait_read_all();  // shared memory must stay valid until the TMA engine has read it
-        }
+        __syncwarp();
+        static_for<A>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            constexpr int OD = P::obs_dim(i);
+            if constexpr (Shape<P>::obs_dense(i)) obs_tile_store<OD>(a.obs[i] + w0 * OD, s_warp + Shape<P>::obs_off(i), lane);
+        });
     } else if (active) {  // the batch's last, partial warp: rows go straight to global memory
         static_for<A>([&](auto ic) {
             constexpr int i = decltype(ic)::value;
@@ -525,9 +526,9 @@ extern "C" int64_t mpe_bytes_per_env_step(mpe_handle h) {
     return 4 * f + p->A;
 }
 
-static bool pdl_enabled() {
-    static const bool on = [] { const char *e = getenv("MPE_B200_PDL"); return e && e[0] == '1'; }();
-    return on;
+static int pdl_mode() {  // 0 = off (default), 1 = late trigger, 2 = early trigger
+    static const int m = [] { const char *e = getenv("MPE_B200_PDL"); return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0; }();
+    return m;
 }
 
 static int launch(mpe_handle h, int mode, StepArgs &args, void *stream) {
@@ -552,7 +553,8 @@ static int launch(mpe_handle h, int mode, StepArgs &args, void *stream) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cfg.numAttrs = pdl_mode() ? 1 : 0;
+    if (pdl_mode() == 2) args.flags |= kFlagPdlEarly;
     void *params[] = {&args};
     cudaError_t e = cudaLaunchKernelExC(&cfg, reinterpret_cast<const void *>(h->prog->fn[mode]), params);
     if (prev != h->device) cudaSetDevice(prev);

@@ -23,6 +23,19 @@ struct WorldRegs {
 
 __host__ __device__ constexpr uint32_t low_bits(int n) { return n >= 32 ? 0xffffffffu : ((1u << n) - 1u); }
 
+// does the descriptor carry exactly the structural flags a program was compiled for?
+template <class P>
+static bool structure_matches(const mpe_desc &d) {
+    for (int i = 0; i < P::A; ++i) {
+        if ((d.agent_collide[i] != 0) != P::agent_collides(i)) return false;
+        if ((d.agent_movable[i] != 0) != P::movable(i)) return false;
+        if ((d.agent_max_speed[i] >= 0) != P::kSpeedLimit) return false;
+    }
+    for (int l = 0; l < P::L; ++l)
+        if ((d.landmark_collide[l] != 0) != P::landmark_collides(l)) return false;
+    return true;
+}
+
 // ---------------------------------------------------------------------------------------------
 // simple.py : 1 agent, 1 landmark, nothing collides
 template <int A_, int L_>
@@ -33,6 +46,10 @@ struct Simple {
     __host__ __device__ static constexpr int obs_dim(int) { return 2 + 2 * L; }   // simple.py:45-50
     __host__ __device__ static constexpr int act_dim(int) { return 5; }
     __host__ __device__ static constexpr bool movable(int) { return true; }
+    // structural flags fixed by simple.py:6-22 (checked against the descriptor in validate())
+    __host__ __device__ static constexpr bool agent_collides(int) { return false; }
+    __host__ __device__ static constexpr bool landmark_collides(int) { return false; }
+    static constexpr bool kSpeedLimit = false;
 
     template <int I, class Wr>
     __device__ __forceinline__ static void observe(const DevDesc &, const W &w, Wr &o) {
@@ -48,7 +65,7 @@ struct Simple {
         }
     }
     static bool validate(const mpe_desc &d) {
-        return d.n_agents == A && d.n_landmarks == L && d.dim_c == 0;
+        return d.n_agents == A && d.n_landmarks == L && d.dim_c == 0 && structure_matches<Simple>(d);
     }
 };
 
@@ -62,6 +79,10 @@ struct Spread {
     __host__ __device__ static constexpr int obs_dim(int) { return 4 + 2 * L + 2 * (A - 1) + DIMC * (A - 1); }
     __host__ __device__ static constexpr int act_dim(int) { return 5; }
     __host__ __device__ static constexpr bool movable(int) { return true; }
+    // structural flags fixed by simple_spread.py:15-26 (checked against the descriptor in validate())
+    __host__ __device__ static constexpr bool agent_collides(int) { return true; }
+    __host__ __device__ static constexpr bool landmark_collides(int) { return false; }
+    static constexpr bool kSpeedLimit = false;
 
     template <int I, class Wr>
     __device__ __forceinline__ static void observe(const DevDesc &, const W &w, Wr &o) {
@@ -98,7 +119,7 @@ struct Spread {
         for (int i = 0; i < A; ++i) {
             float r = base;
             int coll = 0;
-            if ((d.a_collide >> i) & 1u) {                                           // :78-81, a == i included
+            if (agent_collides(i)) {                                                 // :78-81, a == i included
 #pragma unroll
                 for (int a = 0; a < A; ++a)
                     if (hit[i][a]) {
@@ -119,7 +140,7 @@ struct Spread {
         if (d.n_agents != A || d.n_landmarks != L || d.dim_c != DIMC) return false;
         for (int i = 0; i < A; ++i)
             if (!d.agent_movable[i] || !d.agent_silent[i]) return false;
-        return true;
+        return structure_matches<Spread>(d);
     }
 };
 
@@ -137,6 +158,10 @@ struct Tag {
     }
     __host__ __device__ static constexpr int act_dim(int) { return 5; }
     __host__ __device__ static constexpr bool movable(int) { return true; }
+    // structural flags fixed by simple_tag.py:16-33 (checked against the descriptor in validate())
+    __host__ __device__ static constexpr bool agent_collides(int) { return true; }
+    __host__ __device__ static constexpr bool landmark_collides(int) { return true; }
+    static constexpr bool kSpeedLimit = true;
 
     template <int I, class Wr>
     __device__ __forceinline__ static void observe(const DevDesc &, const W &w, Wr &o) {
@@ -169,13 +194,13 @@ struct Tag {
                 for (int g = 0; g < NGOOD; ++g) {
 #pragma unroll
                     for (int a = 0; a < NADV; ++a)
-                        if (((d.a_collide >> i) & 1u) && hit[g][a]) r += 10.0f;
+                        if (agent_collides(i) && hit[g][a]) r += 10.0f;
                     coll += hit[g][i < NADV ? i : 0] ? 1 : 0;                        // benchmark_data :57-66
                 }
             } else {                                                                 // agent_reward :89-113
 #pragma unroll
                 for (int a = 0; a < NADV; ++a)
-                    if (((d.a_collide >> i) & 1u) && hit[i >= NADV ? i - NADV : 0][a]) r -= 10.0f;
+                    if (agent_collides(i) && hit[i >= NADV ? i - NADV : 0][a]) r -= 10.0f;
                 r -= bound_pen(fabsf(w.px[i]));                                      // :109-111
                 r -= bound_pen(fabsf(w.py[i]));
             }
@@ -187,7 +212,7 @@ struct Tag {
         if (d.n_agents != A || d.n_landmarks != L || d.dim_c != DIMC || d.n_adversaries != NADV) return false;
         for (int i = 0; i < A; ++i)
             if (!d.agent_movable[i] || !d.agent_silent[i] || (d.agent_adversary[i] != 0) != adversary(i)) return false;
-        return true;
+        return structure_matches<Tag>(d);
     }
 };
 
@@ -207,6 +232,10 @@ struct WorldComm {
     }
     __host__ __device__ static constexpr int act_dim(int i) { return i == 0 ? 5 + DIMC : 5; }
     __host__ __device__ static constexpr bool movable(int) { return true; }
+    // structural flags fixed by simple_world_comm.py:19-50 (checked against the descriptor in validate())
+    __host__ __device__ static constexpr bool agent_collides(int) { return true; }
+    __host__ __device__ static constexpr bool landmark_collides(int l) { return l < NOBST; }
+    static constexpr bool kSpeedLimit = true;
 
     __device__ __forceinline__ static bool in_forest(const DevDesc &d, const W &w, int i, int f) {
         return is_collision(w.px[i], w.py[i], d.a_size[i], w.lx[FOREST0 + f], w.ly[FOREST0 + f],
@@ -267,13 +296,13 @@ struct WorldComm {
                 for (int g = 0; g < NGOOD; ++g) {
 #pragma unroll
                     for (int a = 0; a < NADV; ++a)
-                        if (((d.a_collide >> i) & 1u) && hit[g][a]) r += 5.0f;       // :193-197
+                        if (agent_collides(i) && hit[g][a]) r += 5.0f;       // :193-197
                     coll += hit[g][i < NADV ? i : 0] ? 1 : 0;                        // benchmark_data :115-123
                 }
             } else {                                                                 // agent_reward :155-183
 #pragma unroll
                 for (int a = 0; a < NADV; ++a)
-                    if (((d.a_collide >> i) & 1u) && hit[i >= NADV ? i - NADV : 0][a]) r -= 5.0f;
+                    if (agent_collides(i) && hit[i >= NADV ? i - NADV : 0][a]) r -= 5.0f;
                 r -= __fmul_rn(2.0f, bound_pen(fabsf(w.px[i])));                               // :176-178
                 r -= __fmul_rn(2.0f, bound_pen(fabsf(w.py[i])));
 #pragma unroll
@@ -301,7 +330,7 @@ struct WorldComm {
             if ((d.agent_leader[i] != 0) != (i == 0)) return false;
             if ((d.agent_silent[i] == 0) != (i == 0)) return false;
         }
-        return true;
+        return structure_matches<WorldComm>(d);
     }
 };
 
