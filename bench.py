@@ -2,7 +2,7 @@
 """bench.py -- env-steps/sec of the multiagent-particle-envs hot path on B200.
 
     python bench.py --gpus N --steps K --warmup W              # this repo (sm_100a kernels)
-    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU arm: the oracle port on host cores
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU arm: the reference path's NumPy port
 
 A "step" is one pass of the hot path (MultiAgentEnv.step: action decode -> World.step -> observation /
 reward / done, environment.py:80-104) over ONE batch of `n_env` worlds = one fused-kernel launch.
@@ -19,7 +19,8 @@ value      device-resident throughput: inputs already in HBM, K fused launches r
 e2e        the same metric through the public API `env.step(host actions)`: pinned H2D of the actions,
            the fused step, D2H of observations / rewards / dones, every step (mpe_step_host)
 roofline   achieved = algorithmic bytes per launch (411 B x n_env) / mean launch time
-cpu_baseline  the CPU oracle port (oracle/mpe_oracle.c, fp64 like the reference) on all host threads
+cpu_baseline  the reference path's per-world NumPy port (oracle/np_port.py), one world per process on all host
+              cores; the C oracle (oracle/mpe_oracle.c) on the same cores is reported under cpu_baseline.c_oracle
 """
 import argparse
 import json
@@ -100,75 +101,113 @@ class ClockSampler(object):
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port on all host threads
+# CPU arm.  Two ports of the reference path live under oracle/ (test + baseline infrastructure):
+#   np_port.py     per-world NumPy float64, the reference's own granularity (one world per process) --
+#                  the stand-in for "the reference's own NumPy path" (measured within 2 % of the real
+#                  reference in the build container: 26.0k vs 26.4k env-steps/s on 8 cores)
+#   mpe_oracle.c   the C checker; ~300x faster than the reference itself; reported alongside
 # ------------------------------------------------------------------------------------------------
-def cpu_oracle_throughput(budget_s, n_sample=N_ENV, steps=None):
-    """env-steps/s of oracle/mpe_oracle.c (fp64, the reference's arithmetic) stepping `n_sample`
-    simple_spread worlds, the batch split over all host threads (ctypes releases the GIL)."""
+def _spread_desc():
+    from multiagent_particle_envs_b200 import make_env
+    return make_env(SCENARIO).world.descriptor()
+
+
+def cpu_numpy_port(budget_s, steps=None, warmup=100):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import np_port
+    cores = len(os.sched_getaffinity(0))
+    desc = _spread_desc()
+    if steps is None:
+        probe, _ = np_port.timed_throughput(desc, min(cores, 4), 20, 200)
+        per_proc = probe / min(cores, 4)
+        steps = int(max(200, min(20000, budget_s * per_proc)))
+    t0 = time.perf_counter()
+    total, rates = np_port.timed_throughput(desc, cores, warmup, steps)
+    dt = time.perf_counter() - t0
+    return {"value": total, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d processes x %d env.step calls of one simple_spread world each (oracle/np_port.py: per-world NumPy "
+                      "float64 restatement at the reference's granularity, softmax actions, reset every 25 steps); %.1f s wall"
+                      % (cores, steps, dt),
+            "per_process": total / cores, "steps_per_process": steps, "seconds": dt}
+
+
+def cpu_c_oracle(budget_s, n_sample=N_ENV):
+    """env-steps/s of oracle/mpe_oracle.c (fp64) stepping n_sample worlds split over all host threads; the
+    step loop runs inside C (ctypes releases the GIL)."""
     import numpy as np
     from concurrent.futures import ThreadPoolExecutor
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     from oracle import Oracle
-    from multiagent_particle_envs_b200 import make_env
-    desc = make_env(SCENARIO).world.descriptor()
+    desc = _spread_desc()
     cores = len(os.sched_getaffinity(0))
     rng = np.random.RandomState(0)
     A, L = 3, 3
-    chunks = []
     per = (n_sample + cores - 1) // cores
+    chunks = []
     for c in range(cores):
         m = min(per, n_sample - c * per)
         if m <= 0:
             break
         pv = np.zeros((m, A, 4))
         pv[:, :, :2] = rng.uniform(-1, 1, (m, A, 2))
-        lm = rng.uniform(-1, 1, (m, L, 2))
         logits = rng.randn(m, A, 5)
-        act = np.exp(logits) / np.exp(logits).sum(-1, keepdims=True)
-        chunks.append([Oracle(desc, "f64"), pv, lm, np.zeros((m, A, 2)), act.reshape(m, 15)])
-
-    def run(ch):
-        orc, pv, lm, comm, act = ch
-        ch[1], ch[3], *_ = orc.step(pv, lm, comm, act, flags=1)
-
+        act = np.ascontiguousarray((np.exp(logits) / np.exp(logits).sum(-1, keepdims=True)).reshape(m, 15))
+        chunks.append((Oracle(desc, "f64"), pv, rng.uniform(-1, 1, (m, L, 2)), np.zeros((m, A, 2)), act))
     pool = ThreadPoolExecutor(len(chunks))
-    list(pool.map(run, chunks))  # warm-up
-    t0 = time.perf_counter()
-    list(pool.map(run, chunks))
-    one = time.perf_counter() - t0
-    if steps is None:
-        steps = max(1, min(2000, int(budget_s / max(one, 1e-6))))
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        list(pool.map(run, chunks))
-    dt = time.perf_counter() - t0
+
+    def run(steps):
+        t0 = time.perf_counter()
+        list(pool.map(lambda ch: ch[0].rollout(ch[1], ch[2], ch[3], ch[4], steps, 1), chunks))
+        return time.perf_counter() - t0
+
+    run(1)
+    one = run(2) / 2
+    steps = int(max(2, min(5000, budget_s / max(one, 1e-6))))
+    dt = run(steps)
     pool.shutdown()
     return {"value": n_sample * steps / dt, "unit": UNIT, "cores": len(chunks), "kind": "port",
-            "sample": "%d steps x %d worlds of the same workload through oracle/mpe_oracle.c (fp64 C restatement of "
-                      "the reference's NumPy path, one thread per core); %.1f s" % (steps, n_sample, dt),
-            "seconds": dt, "steps": steps, "n_sample": n_sample}
+            "sample": "%d steps x %d worlds through oracle/mpe_oracle.c (fp64 C restatement, step loop in C, one thread "
+                      "per core); %.1f s" % (steps, n_sample, dt)}
+
+
+def cpu_baseline_block(numpy_seconds, c_seconds):
+    cb = cpu_numpy_port(numpy_seconds)
+    out = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    out["per_process"] = cb["per_process"]
+    if c_seconds > 0:
+        c = cpu_c_oracle(c_seconds)
+        out["c_oracle"] = {k: c[k] for k in ("value", "unit", "cores", "sample")}
+    return out, cb
 
 
 def run_reference_arm(args, rank, world):
+    """The reference's CPU path on this box's host cores: the per-world NumPy port, one world per process
+    on every core.  One bench "step" here = one env.step in each of the `cores` worlds (a bounded sample of
+    the 65536-world batch); the timed run is capped at ~90 s."""
     if rank != 0:
         return
     t_all = time.perf_counter()
-    probe = cpu_oracle_throughput(1.0, steps=2)
-    total = args.steps + args.warmup
-    # bounded sample per step so that the whole K+W run stays within ~90 s
-    n_sample = int(max(256, min(N_ENV, probe["value"] * 90.0 / max(total, 1))))
-    res = cpu_oracle_throughput(0, n_sample=n_sample, steps=args.warmup) if args.warmup else None
-    res = cpu_oracle_throughput(0, n_sample=n_sample, steps=args.steps)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import np_port
+    cores = len(os.sched_getaffinity(0))
+    probe, _ = np_port.timed_throughput(_spread_desc(), min(cores, 4), 20, 200)
+    per_proc = probe / min(cores, 4)
+    steps_timed = int(max(50, min(args.steps, 90.0 * per_proc)))
+    res = cpu_numpy_port(0, steps=steps_timed, warmup=min(max(args.warmup, 3), 500))
     cb = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    cb["per_process"] = res["per_process"]
+    c = cpu_c_oracle(5.0)
+    cb["c_oracle"] = {k: c[k] for k in ("value", "unit", "cores", "sample")}
     line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * res["seconds"] / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args.gpus, 1), "cpu_baseline": cb,
+            "steps": args.steps, "steps_timed_per_process": steps_timed, "warmup": args.warmup,
+            "ms_per_step": 1e3 * cores / res["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args.gpus, 1), "cpu_baseline": cb,
             "agent_steps_per_sec": 3 * res["value"],
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t_all,
-            "note": "reference arm = CPU oracle port (the Python reference cannot travel to the GPU box); each step "
-                    "is a %d-world sample of the 65536-world batch" % n_sample}
+            "note": "reference arm = oracle/np_port.py, the per-world NumPy port of the reference path (the Python reference "
+                    "itself cannot travel to the GPU box); %d processes, one world each; the C oracle on the same cores is "
+                    "reported under cpu_baseline.c_oracle" % cores}
     print(json.dumps(line), flush=True)
 
 
@@ -295,7 +334,7 @@ def run_b200_arm(args, rank, local_rank, world):
                 traffic = json.load(open(tp)).get("simple_spread_65536_dram_bytes_per_launch")
             except Exception:  # noqa: BLE001
                 traffic = None
-        cpu = cpu_oracle_throughput(args.cpu_seconds) if world == 1 and args.cpu_seconds > 0 else None
+        cpu = cpu_baseline_block(args.cpu_seconds, 5.0)[0] if world == 1 and args.cpu_seconds > 0 else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": 1e3 * launch_s, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -311,7 +350,7 @@ def run_b200_arm(args, rank, local_rank, world):
             "per_rank": per_rank,
         }
         if cpu is not None:
-            line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -325,7 +364,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ring", type=int, default=12)
     ap.add_argument("--e2e-steps", type=int, default=200)
-    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

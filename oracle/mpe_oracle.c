@@ -451,3 +451,11 @@ void FN(mpe_oracle_step)(const mpe_desc *d, int64_t n, real *pv, const real *lm,
                       obs + w * so, rew + w * A, done + w * A, info ? info + w * A * idim : 0, flags);
     }
 }
+
+/* `steps` consecutive MultiAgentEnv.step calls on the same action batch, entirely in C (used by
+ * bench.py to time this port on all host threads without returning to Python between steps) */
+void FN(mpe_oracle_rollout)(const mpe_desc *d, int64_t n, real *pv, const real *lm, real *comm,
+                            const real *act, int steps, real *obs, real *rew, uint8_t *done, uint32_t flags) {
+    for (int t = 0; t < steps; ++t)
+        FN(mpe_oracle_step)(d, n, pv, lm, comm, 0, 0, act, obs, rew, done, 0, flags);
+}

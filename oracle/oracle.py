@@ -78,6 +78,18 @@ class Oracle(object):
            self._p(done), self._p(info) if self.info_dim > 0 else None, ctypes.c_uint32(flags))
         return pv, comm, obs, rew, done, info[:, :, :self.info_dim]
 
+    def rollout(self, pv, lm, comm, act, steps, flags=0):
+        """`steps` env steps in C on the same actions; arrays are updated in place (already in the oracle dtype)"""
+        n = pv.shape[0]
+        if not hasattr(self, "_ro") or self._ro[0].shape[0] != n:
+            self._ro = self.empty_outputs(n)
+        obs, rew, done, _ = self._ro
+        fn = self._f("mpe_oracle_rollout")
+        fn.restype = None
+        fn(ctypes.byref(self.desc), ctypes.c_int64(n), self._p(pv), self._p(lm), self._p(comm), self._p(act),
+           ctypes.c_int(steps), self._p(obs), self._p(rew), self._p(done), ctypes.c_uint32(flags))
+        return obs, rew, done
+
     def observe(self, pv, lm, comm, flags=0, goal=None):
         n = pv.shape[0]
         pv = self._arr(pv, (n, self.A, 4))

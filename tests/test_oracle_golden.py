@@ -76,3 +76,28 @@ def test_known_answers_of_survey():
         np.testing.assert_allclose(obs[0], k[name + "/obs"], rtol=1e-12, atol=1e-60)
         np.testing.assert_allclose(rew[0], k[name + "/rew"], rtol=1e-12, atol=1e-15)
         assert np.array_equal(done[0], k[name + "/done"])
+
+
+@pytest.mark.parametrize("tag", TAGS)
+def test_numpy_port_matches_reference(tag):
+    """oracle/np_port.py (the per-world NumPy stand-in for the reference's own path that bench.py times)"""
+    import np_port
+    g = load_golden(tag)
+    spec = np_port.WorldSpec(descriptor(tag))
+    shared = bool(int(g["prop_shared_reward"]))
+    W, T = g["act"].shape[:2]
+    adims = [int(x) for x in g["prop_act_dims"]]
+    for w in range(min(W, 4)):
+        pos = np.concatenate([g["pv0"][w][:, 0:2], g["lm"][w]]).copy()
+        vel = g["pv0"][w][:, 2:4].copy()
+        comm = g["comm0"][w].copy()
+        for t in range(T):
+            acts, c0 = [], 0
+            for dmn in adims:
+                acts.append(g["act"][w, t, c0:c0 + dmn])
+                c0 += dmn
+            obs, rew, done = np_port.env_step(spec, pos, vel, comm, acts, shared)
+            np.testing.assert_allclose(np.concatenate(obs), g["obs"][w, t], rtol=1e-11, atol=1e-13)
+            np.testing.assert_allclose(np.array(rew, dtype=np.float64), g["rew"][w, t], rtol=1e-11, atol=1e-12)
+            np.testing.assert_allclose(pos[:spec.A], g["pv"][w, t][:, 0:2], rtol=1e-11, atol=1e-13)
+            assert not any(done)
