@@ -30,6 +30,10 @@ import sys
 import threading
 import time
 
+# the CPU arms run one world per process: keep NumPy / torch thread pools from oversubscribing the host
+for _v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+    os.environ.setdefault(_v, "1")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
