@@ -179,6 +179,10 @@ __global__ void __launch_bounds__(kMaxThreads) mpe_kernel(const __grid_constant_
 #pragma unroll
             for (int q = 0; q < NC; ++q) w.c[q] = a.comm[q * n + wi];
         }
+        if constexpr ((MODE == kObserve || MODE == kFusedStep) && P::G > 0) {
+#pragma unroll
+            for (int q = 0; q < P::G; ++q) w.g[q] = a.goal[q * n + wi];
+        }
     }
 
     float ux[A], uy[A];
@@ -402,6 +406,11 @@ static const Program *programs(int *count) {
         make_program<Spread<5>>(), make_program<Spread<6>>(),
         make_program<Tag<3, 1, 2>>(),
         make_program<WorldComm<4, 2, 1, 2>>(),
+        make_program<Adversary<1, 2, 2>>(),
+        make_program<Push<1, 1, 2>>(),
+        make_program<SpeakerListener>(),
+        make_program<Reference>(),
+        make_program<Crypto>(),
     };
     *count = static_cast<int>(sizeof(table) / sizeof(table[0]));
     return table;
@@ -518,11 +527,11 @@ extern "C" int mpe_info_dim(mpe_handle h) { return h ? h->prog->INFO : MPE_ERR_B
 
 extern "C" int64_t mpe_bytes_per_env_step(mpe_handle h) {
     if (!h) return MPE_ERR_BAD_ARG;
-    // read agent pos+vel, landmark pos, actions; write agent pos+vel, obs,
-    // rewards (+ speaker comm state), 1 done byte per agent
+    // read agent pos+vel, landmark pos, goal indices, actions; write pos+vel of the movable
+    // agents, observations, rewards, speaker comm state, 1 done byte per agent
     const Program *p = h->prog;
-    int64_t f = 4 * p->A + 2 * p->L + 4 * p->A + p->A + p->NS * p->DIMC;
-    for (int i = 0; i < p->A; ++i) f += p->act_dim[i] + p->obs_dim[i];
+    int64_t f = 4 * p->A + 2 * p->L + p->G + p->A + p->NS * p->DIMC;
+    for (int i = 0; i < p->A; ++i) f += p->act_dim[i] + p->obs_dim[i] + (h->desc.agent_movable[i] ? 4 : 0);
     return 4 * f + p->A;
 }
 

@@ -14,12 +14,22 @@
 
 namespace mpe {
 
-template <int A_, int L_, int NC_>
+template <int A_, int L_, int NC_, int NG_ = 0>
 struct WorldRegs {
     float px[A_], py[A_], vx[A_], vy[A_];
     float lx[L_], ly[L_];
     float c[NC_ > 0 ? NC_ : 1];  // comm state of the speakers, [speaker][dim_c]
+    int g[NG_ > 0 ? NG_ : 1];    // per-world goal indices
 };
+
+// v[idx] for a per-lane index without dynamic register indexing (select chain, N <= 8)
+template <int N>
+__device__ __forceinline__ float pick(const float (&v)[N], int idx) {
+    float r = v[0];
+#pragma unroll
+    for (int k = 1; k < N; ++k) r = (idx == k) ? v[k] : r;
+    return r;
+}
 
 __host__ __device__ constexpr uint32_t low_bits(int n) { return n >= 32 ? 0xffffffffu : ((1u << n) - 1u); }
 
@@ -331,6 +341,270 @@ struct WorldComm {
             if ((d.agent_silent[i] == 0) != (i == 0)) return false;
         }
         return structure_matches<WorldComm>(d);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// simple_adversary.py : NADV adversaries (first), NGOOD good agents, L landmarks, goal = g[0]
+template <int NADV_, int NGOOD_, int L_>
+struct Adversary {
+    static constexpr int NADV = NADV_, NGOOD = NGOOD_;
+    static constexpr int A = NADV + NGOOD, L = L_, DIMC = 2, NS = 0, INFO = L_ + 1, G = 1;
+    static constexpr int kScenario = MPE_SCN_ADVERSARY;
+    using W = WorldRegs<A, L, 0, G>;
+    __host__ __device__ static constexpr bool adversary(int i) { return i < NADV; }
+    __host__ __device__ static constexpr int obs_dim(int i) { return (adversary(i) ? 0 : 2) + 2 * L + 2 * (A - 1); }
+    __host__ __device__ static constexpr int act_dim(int) { return 5; }
+    __host__ __device__ static constexpr bool movable(int) { return true; }
+    __host__ __device__ static constexpr bool agent_collides(int) { return false; }    // simple_adversary.py:24
+    __host__ __device__ static constexpr bool landmark_collides(int) { return false; }
+    static constexpr bool kSpeedLimit = false;
+
+    template <int I, class Wr>
+    __device__ __forceinline__ static void observe(const DevDesc &, const W &w, Wr &o) {
+        if (!adversary(I)) o.put2(pick(w.lx, w.g[0]) - w.px[I], pick(w.ly, w.g[0]) - w.py[I]);   // :136
+#pragma unroll
+        for (int l = 0; l < L; ++l) o.put2(w.lx[l] - w.px[I], w.ly[l] - w.py[I]);                  // :123-125
+#pragma unroll
+        for (int j = 0; j < A; ++j)
+            if (j != I) o.put2(w.px[j] - w.px[I], w.py[j] - w.py[I]);                              // :131-133
+    }
+    __device__ __forceinline__ static void reward(const DevDesc &, const W &w, float (&rew)[A], float *info) {
+        const float gx = pick(w.lx, w.g[0]), gy = pick(w.ly, w.g[0]);
+        float adv_sum = 0.0f, good_min = 0.0f;
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+            const float dd = dist2d(w.px[a], w.py[a], gx, gy);
+            if (adversary(a)) adv_sum += dd;                                                        // :83
+            else good_min = (a == NADV) ? dd : (dd < good_min ? dd : good_min);                     // :93-94
+        }
+#pragma unroll
+        for (int i = 0; i < A; ++i) {
+            const float dx = __fsub_rn(w.px[i], gx), dy = __fsub_rn(w.py[i], gy);
+            const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+            rew[i] = adversary(i) ? -d2 : __fadd_rn(-good_min, adv_sum);                            // :105, :107-118
+            if (info) {                                                                             // :61-70
+#pragma unroll
+                for (int q = 0; q < INFO; ++q) info[i * INFO + q] = 0.0f;
+                if (adversary(i)) {
+                    info[i * INFO] = d2;
+                } else {
+#pragma unroll
+                    for (int l = 0; l < L; ++l) {
+                        const float ex = __fsub_rn(w.px[i], w.lx[l]), ey = __fsub_rn(w.py[i], w.ly[l]);
+                        info[i * INFO + l] = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+                    }
+                    info[i * INFO + L] = d2;
+                }
+            }
+        }
+    }
+    static bool validate(const mpe_desc &d) {
+        if (d.n_agents != A || d.n_landmarks != L || d.dim_c != DIMC || d.n_adversaries != NADV) return false;
+        for (int i = 0; i < A; ++i)
+            if (!d.agent_silent[i] || (d.agent_adversary[i] != 0) != adversary(i)) return false;
+        return structure_matches<Adversary>(d);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// simple_push.py : NADV adversaries (first), NGOOD good agents (all collide), L landmarks, goal = g[0]
+template <int NADV_, int NGOOD_, int L_>
+struct Push {
+    static constexpr int NADV = NADV_, NGOOD = NGOOD_;
+    static constexpr int A = NADV + NGOOD, L = L_, DIMC = 2, NS = 0, INFO = 0, G = 1;
+    static constexpr int kScenario = MPE_SCN_PUSH;
+    using W = WorldRegs<A, L, 0, G>;
+    __host__ __device__ static constexpr bool adversary(int i) { return i < NADV; }
+    __host__ __device__ static constexpr int obs_dim(int i) {                        // simple_push.py:76-96
+        return adversary(i) ? 2 + 2 * L + 2 * (A - 1) : 2 + 2 + 3 + 2 * L + 3 * L + 2 * (A - 1);
+    }
+    __host__ __device__ static constexpr int act_dim(int) { return 5; }
+    __host__ __device__ static constexpr bool movable(int) { return true; }
+    __host__ __device__ static constexpr bool agent_collides(int) { return true; }     // simple_push.py:19
+    __host__ __device__ static constexpr bool landmark_collides(int) { return false; }
+    static constexpr bool kSpeedLimit = false;
+
+    template <int I, class Wr>
+    __device__ __forceinline__ static void observe(const DevDesc &, const W &w, Wr &o) {
+        o.put2(w.vx[I], w.vy[I]);
+        if (!adversary(I)) {
+            o.put2(pick(w.lx, w.g[0]) - w.px[I], pick(w.ly, w.g[0]) - w.py[I]);       // :93
+#pragma unroll
+            for (int c = 0; c < 3; ++c) o.put(w.g[0] + 1 == c ? 0.25f + 0.5f : 0.25f); // agent.color (:47-53)
+        }
+#pragma unroll
+        for (int l = 0; l < L; ++l) o.put2(w.lx[l] - w.px[I], w.ly[l] - w.py[I]);
+        if (!adversary(I)) {
+#pragma unroll
+            for (int l = 0; l < L; ++l)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) o.put(c == l + 1 ? 0.1f + 0.8f : 0.1f);   // landmark colours (:34-37)
+        }
+#pragma unroll
+        for (int j = 0; j < A; ++j)
+            if (j != I) o.put2(w.px[j] - w.px[I], w.py[j] - w.py[I]);
+    }
+    __device__ __forceinline__ static void reward(const DevDesc &, const W &w, float (&rew)[A], float *) {
+        const float gx = pick(w.lx, w.g[0]), gy = pick(w.ly, w.g[0]);
+        float dg[A];
+#pragma unroll
+        for (int a = 0; a < A; ++a) dg[a] = dist2d(w.px[a], w.py[a], gx, gy);
+        float good_min = dg[NADV];
+#pragma unroll
+        for (int a = NADV + 1; a < A; ++a) good_min = dg[a] < good_min ? dg[a] : good_min;
+#pragma unroll
+        for (int i = 0; i < A; ++i) rew[i] = adversary(i) ? __fsub_rn(good_min, dg[i]) : -dg[i];   // :62-74
+    }
+    static bool validate(const mpe_desc &d) {
+        if (d.n_agents != A || d.n_landmarks != L || d.dim_c != DIMC || d.n_adversaries != NADV) return false;
+        for (int i = 0; i < A; ++i)
+            if (!d.agent_silent[i] || (d.agent_adversary[i] != 0) != adversary(i)) return false;
+        return structure_matches<Push>(d);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// simple_speaker_listener.py : agent 0 = immovable speaker, agent 1 = silent listener, goal = g[0]
+struct SpeakerListener {
+    static constexpr int A = 2, L = 3, DIMC = 3, NS = 1, INFO = 0, G = 1;
+    static constexpr int kScenario = MPE_SCN_SPEAKER_LISTENER;
+    using W = WorldRegs<A, L, NS * DIMC, G>;
+    __host__ __device__ static constexpr int obs_dim(int i) { return i == 0 ? 3 : 2 + 2 * L + DIMC; }
+    __host__ __device__ static constexpr bool movable(int i) { return i == 1; }
+    __host__ __device__ static constexpr int act_dim(int i) { return i == 0 ? DIMC : 5; }
+    __host__ __device__ static constexpr bool agent_collides(int) { return false; }
+    __host__ __device__ static constexpr bool landmark_collides(int) { return false; }
+    static constexpr bool kSpeedLimit = false;
+
+    template <int I, class Wr>
+    __device__ __forceinline__ static void observe(const DevDesc &, const W &w, Wr &o) {
+        if (I == 0) {                                                                // :70-72, 87-88
+#pragma unroll
+            for (int c = 0; c < 3; ++c) o.put(w.g[0] == c ? 0.65f : 0.15f);
+        } else {                                                                     // :90-92
+            o.put2(w.vx[1], w.vy[1]);
+#pragma unroll
+            for (int l = 0; l < L; ++l) o.put2(w.lx[l] - w.px[1], w.ly[l] - w.py[1]);
+#pragma unroll
+            for (int q = 0; q < DIMC; ++q) o.put(w.c[q]);
+        }
+    }
+    __device__ __forceinline__ static void reward(const DevDesc &, const W &w, float (&rew)[A], float *) {
+        const float dx = __fsub_rn(w.px[1], pick(w.lx, w.g[0])), dy = __fsub_rn(w.py[1], pick(w.ly, w.g[0]));
+        rew[0] = rew[1] = -__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));          // :63-67
+    }
+    static bool validate(const mpe_desc &d) {
+        if (d.n_agents != A || d.n_landmarks != L || d.dim_c != DIMC) return false;
+        if (d.agent_silent[0] || !d.agent_silent[1]) return false;
+        return structure_matches<SpeakerListener>(d);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// simple_reference.py : 2 agents that move and speak; g[i] = agents[i].goal_b, goal_a = the other agent
+struct Reference {
+    static constexpr int A = 2, L = 3, DIMC = 10, NS = 2, INFO = 0, G = 2;
+    static constexpr int kScenario = MPE_SCN_REFERENCE;
+    using W = WorldRegs<A, L, NS * DIMC, G>;
+    __host__ __device__ static constexpr int obs_dim(int) { return 2 + 2 * L + 3 + DIMC * (A - 1); }
+    __host__ __device__ static constexpr bool movable(int) { return true; }
+    __host__ __device__ static constexpr int act_dim(int) { return 5 + DIMC; }
+    __host__ __device__ static constexpr bool agent_collides(int) { return false; }
+    __host__ __device__ static constexpr bool landmark_collides(int) { return false; }
+    static constexpr bool kSpeedLimit = false;
+
+    template <int I, class Wr>
+    __device__ __forceinline__ static void observe(const DevDesc &, const W &w, Wr &o) {
+        o.put2(w.vx[I], w.vy[I]);                                                    // :80
+#pragma unroll
+        for (int l = 0; l < L; ++l) o.put2(w.lx[l] - w.px[I], w.ly[l] - w.py[I]);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) o.put(w.g[I] == c ? 0.75f : 0.25f);              // goal_b colour :64-66
+#pragma unroll
+        for (int q = 0; q < DIMC; ++q) o.put(w.c[(1 - I) * DIMC + q]);               // :76-79
+    }
+    __device__ __forceinline__ static void reward(const DevDesc &, const W &w, float (&rew)[A], float *) {
+#pragma unroll
+        for (int i = 0; i < A; ++i) {                                                // :55-59
+            const float dx = __fsub_rn(w.px[1 - i], pick(w.lx, w.g[i])), dy = __fsub_rn(w.py[1 - i], pick(w.ly, w.g[i]));
+            rew[i] = -__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        }
+    }
+    static bool validate(const mpe_desc &d) {
+        if (d.n_agents != A || d.n_landmarks != L || d.dim_c != DIMC) return false;
+        if (d.agent_silent[0] || d.agent_silent[1]) return false;
+        return structure_matches<Reference>(d);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// simple_crypto.py : Eve (0, adversary), Bob (1), Alice (2, speaker); nobody moves; g[0] = goal, g[1] = key
+struct Crypto {
+    static constexpr int A = 3, L = 2, DIMC = 4, NS = 3, INFO = 2 * DIMC, G = 2;
+    static constexpr int kScenario = MPE_SCN_CRYPTO;
+    using W = WorldRegs<A, L, NS * DIMC, G>;
+    __host__ __device__ static constexpr bool adversary(int i) { return i == 0; }
+    __host__ __device__ static constexpr int obs_dim(int i) { return i == 0 ? DIMC : 2 * DIMC; }
+    __host__ __device__ static constexpr bool movable(int) { return false; }
+    __host__ __device__ static constexpr int act_dim(int) { return DIMC; }
+    __host__ __device__ static constexpr bool agent_collides(int) { return false; }
+    __host__ __device__ static constexpr bool landmark_collides(int) { return false; }
+    static constexpr bool kSpeedLimit = false;
+
+    template <int I, class Wr>
+    __device__ __forceinline__ static void observe(const DevDesc &, const W &w, Wr &o) {
+        if (I == 2) {                                                                // speaker :157-162
+#pragma unroll
+            for (int q = 0; q < DIMC; ++q) o.put(w.g[0] == q ? 1.0f : 0.0f);
+#pragma unroll
+            for (int q = 0; q < DIMC; ++q) o.put(w.g[1] == q ? 1.0f : 0.0f);
+        } else if (I == 1) {                                                         // listener :163-168
+#pragma unroll
+            for (int q = 0; q < DIMC; ++q) o.put(w.g[1] == q ? 1.0f : 0.0f);
+#pragma unroll
+            for (int q = 0; q < DIMC; ++q) o.put(w.c[2 * DIMC + q]);
+        } else {                                                                     // adversary :169-174
+#pragma unroll
+            for (int q = 0; q < DIMC; ++q) o.put(w.c[2 * DIMC + q]);
+        }
+    }
+    __device__ __forceinline__ static void reward(const DevDesc &, const W &w, float (&rew)[A], float *info) {
+        float err[A];
+        bool spoke[A];
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+            float e = 0.0f;
+            bool nz = false;
+#pragma unroll
+            for (int q = 0; q < DIMC; ++q) {
+                const float df = __fsub_rn(w.c[a * DIMC + q], w.g[0] == q ? 1.0f : 0.0f);
+                e = __fadd_rn(e, __fmul_rn(df, df));
+                nz = nz || (w.c[a * DIMC + q] != 0.0f);
+            }
+            err[a] = e;
+            spoke[a] = nz;
+        }
+        const float good_rew = spoke[1] ? -err[1] : 0.0f;                             // :98-103
+        const float adv_rew = spoke[0] ? err[0] : 0.0f;                              // :104-109
+        rew[0] = spoke[0] ? -err[0] : 0.0f;                                          // :115-121
+        rew[1] = rew[2] = __fadd_rn(adv_rew, good_rew);                              // :110
+        if (info) {                                                                  // :66-67
+#pragma unroll
+            for (int i = 0; i < A; ++i) {
+#pragma unroll
+                for (int q = 0; q < DIMC; ++q) {
+                    info[i * INFO + q] = w.c[i * DIMC + q];
+                    info[i * INFO + DIMC + q] = w.g[0] == q ? 1.0f : 0.0f;
+                }
+            }
+        }
+    }
+    static bool validate(const mpe_desc &d) {
+        if (d.n_agents != A || d.n_landmarks != L || d.dim_c != DIMC || d.n_adversaries != 1) return false;
+        for (int i = 0; i < A; ++i)
+            if (d.agent_silent[i] || (d.agent_adversary[i] != 0) != adversary(i)) return false;
+        return structure_matches<Crypto>(d);
     }
 };
 

@@ -215,16 +215,27 @@ class NativeWorld(ShapeHandle):
 
     # ---- benchmark_data (e.g. simple_spread.py:47-63) -----------------------------------------
     def benchmark_data(self, i, batched, out=None):
+        """scenario.benchmark_data(agent i) from the info channel, in the reference's return shape"""
         out = out or self.out
         sc = self.desc.scenario
         if out.info is None:
             return {}
-        info = out.info[i]
+        info = out.info[i]                     # [info_dim, N]
+        adv = bool(self.desc.agent_adversary[i])
+        L, C = self.n_landmarks, self.dim_c
         if batched:
-            if sc == _lib.SCN_SPREAD:
+            if sc == _lib.SCN_SPREAD:           # (rew, collisions, min_dists, occupied_landmarks)
                 return (info[0], info[1], info[2], info[3])
+            if sc == _lib.SCN_ADVERSARY:        # adversary: |p - goal|^2; good: (|p - lm_l|^2 ..., |p - goal|^2)
+                return info[0] if adv else tuple(info[q] for q in range(L + 1))
+            if sc == _lib.SCN_CRYPTO:           # (agent.state.c, goal colour)
+                return (info[0:C].t(), info[C:2 * C].t())
             return info[0]
         v = info[:, 0].detach().to("cpu").numpy().astype(np.float64)
-        if sc == _lib.SCN_SPREAD:   # (rew, collisions, min_dists, occupied_landmarks)
+        if sc == _lib.SCN_SPREAD:
             return (float(v[0]), int(v[1]), float(v[2]), int(v[3]))
+        if sc == _lib.SCN_ADVERSARY:
+            return float(v[0]) if adv else tuple(float(x) for x in v[:L + 1])
+        if sc == _lib.SCN_CRYPTO:
+            return (v[0:C].copy(), v[C:2 * C].copy())
         return int(v[0])

@@ -67,7 +67,20 @@ int FN(mpe_oracle_obs_dim)(const mpe_desc *d, int i) {
         int base = 4 + 2 * L + 2 * (A - 1) + 2 * n_good_others + 2;
         return d->agent_adversary[i] ? base + d->dim_c : base;
     }
+    case MPE_SCN_ADVERSARY: return d->agent_adversary[i] ? 2 * L + 2 * (A - 1) : 2 + 2 * L + 2 * (A - 1);  /* simple_adversary.py:121-139 */
+    case MPE_SCN_PUSH: return d->agent_adversary[i] ? 2 + 2 * L + 2 * (A - 1) : 2 + 2 + 3 + 2 * L + 3 * L + 2 * (A - 1);  /* simple_push.py:76-96 */
+    case MPE_SCN_SPEAKER_LISTENER: return d->agent_movable[i] ? 2 + 2 * L + d->dim_c : 3;  /* simple_speaker_listener.py:69-92 */
+    case MPE_SCN_REFERENCE: return 2 + 2 * L + 3 + d->dim_c * (A - 1);   /* simple_reference.py:61-80 */
+    case MPE_SCN_CRYPTO: return i == 2 ? 2 * d->dim_c : (d->agent_adversary[i] ? d->dim_c : 2 * d->dim_c);  /* simple_crypto.py:124-169 */
     default: return -1;
+    }
+}
+
+int FN(mpe_oracle_num_goals)(const mpe_desc *d) {
+    switch (d->scenario) {
+    case MPE_SCN_ADVERSARY: case MPE_SCN_PUSH: case MPE_SCN_SPEAKER_LISTENER: return 1;
+    case MPE_SCN_REFERENCE: case MPE_SCN_CRYPTO: return 2;
+    default: return 0;
     }
 }
 
@@ -77,6 +90,9 @@ int FN(mpe_oracle_info_dim)(const mpe_desc *d) {
     case MPE_SCN_SPREAD: return 4;      /* simple_spread.py:47-63 */
     case MPE_SCN_TAG: return 1;         /* simple_tag.py:57-66   */
     case MPE_SCN_WORLD_COMM: return 1;  /* simple_world_comm.py:115-123 */
+    case MPE_SCN_ADVERSARY: return d->n_landmarks + 1;   /* simple_adversary.py:61-70 */
+    case MPE_SCN_CRYPTO: return 2 * d->dim_c;            /* simple_crypto.py:66-67 */
+    case MPE_SCN_PUSH: case MPE_SCN_SPEAKER_LISTENER: case MPE_SCN_REFERENCE: return 0;
     default: return -1;
     }
 }
@@ -384,16 +400,158 @@ static void observe_world_comm(const mpe_desc *d, const real *pv, const real *lm
     }
 }
 
+/* ---- simple_adversary.py ----------------------------------------------------------------- */
+/* goal[0] = index of the goal landmark (np.random.choice(world.landmarks), :44) */
+static void observe_adversary(const mpe_desc *d, const real *pv, const real *lm, const int32_t *goal,
+                              real *obs, real *rew, real *info) {
+    const int A = d->n_agents, L = d->n_landmarks, g = goal[0], I = L + 1;
+    real *o = obs;
+    /* agent_reward terms (:76-105): shaped, sum over adversaries / min over good agents */
+    real adv_sum = 0, good_min = 0;
+    int first = 1;
+    for (int a = 0; a < A; ++a) {
+        real dd = dist2d(PX(a), PY(a), LX(g), LY(g));
+        if (d->agent_adversary[a]) adv_sum += dd;                          /* :83 */
+        else { if (first || dd < good_min) good_min = dd; first = 0; }      /* :93-94 */
+    }
+    for (int i = 0; i < A; ++i) {
+        if (!d->agent_adversary[i]) { *o++ = LX(g) - PX(i); *o++ = LY(g) - PY(i); }          /* :136 */
+        for (int l = 0; l < L; ++l) { *o++ = LX(l) - PX(i); *o++ = LY(l) - PY(i); }           /* :123-125 */
+        for (int j = 0; j < A; ++j) if (j != i) { *o++ = PX(j) - PX(i); *o++ = PY(j) - PY(i); }   /* :131-133 */
+        real dx = PX(i) - LX(g), dy = PY(i) - LY(g);
+        real d2 = dx * dx + dy * dy;
+        if (d->agent_adversary[i]) rew[i] = -d2;                            /* adversary_reward :107-118 */
+        else rew[i] = -good_min + adv_sum;                                  /* :105 pos_rew + adv_rew */
+        if (info) {                                                         /* benchmark_data :61-70 */
+            for (int q = 0; q < I; ++q) info[i * I + q] = 0;
+            if (d->agent_adversary[i]) info[i * I] = d2;
+            else {
+                for (int l = 0; l < L; ++l) { real ex = PX(i) - LX(l), ey = PY(i) - LY(l); info[i * I + l] = ex * ex + ey * ey; }
+                info[i * I + L] = d2;
+            }
+        }
+    }
+}
+
+/* ---- simple_push.py ---------------------------------------------------------------------- */
+static void observe_push(const mpe_desc *d, const real *pv, const real *lm, const int32_t *goal, real *obs, real *rew) {
+    const int A = d->n_agents, L = d->n_landmarks, g = goal[0];
+    real *o = obs;
+    real good_min = 0;
+    int first = 1;
+    for (int a = 0; a < A; ++a) if (!d->agent_adversary[a]) {              /* adversary_reward :68-69 */
+        real dd = dist2d(PX(a), PY(a), LX(g), LY(g));
+        if (first || dd < good_min) good_min = dd;
+        first = 0;
+    }
+    for (int i = 0; i < A; ++i) {
+        *o++ = VX(i); *o++ = VY(i);
+        if (!d->agent_adversary[i]) {                                       /* :93-94 */
+            *o++ = LX(g) - PX(i); *o++ = LY(g) - PY(i);
+            /* agent.color = [0.25]*3 with color[goal.index + 1] += 0.5 (:47-53) */
+            for (int c = 0; c < 3; ++c) *o++ = (c == g + 1) ? R(0.25) + R(0.5) : R(0.25);
+        }
+        for (int l = 0; l < L; ++l) { *o++ = LX(l) - PX(i); *o++ = LY(l) - PY(i); }
+        if (!d->agent_adversary[i])                                         /* entity_color: [0.1]*3, color[i+1] += 0.8 (:34-37) */
+            for (int l = 0; l < L; ++l) for (int c = 0; c < 3; ++c) *o++ = (c == l + 1) ? R(0.1) + R(0.8) : R(0.1);
+        for (int j = 0; j < A; ++j) if (j != i) { *o++ = PX(j) - PX(i); *o++ = PY(j) - PY(i); }
+        if (d->agent_adversary[i])                                          /* :66-74 */
+            rew[i] = good_min - dist2d(LX(g), LY(g), PX(i), PY(i));
+        else                                                                /* :62-64 */
+            rew[i] = -dist2d(PX(i), PY(i), LX(g), LY(g));
+    }
+}
+
+/* ---- simple_speaker_listener.py ---------------------------------------------------------- */
+/* goal[0] = agents[0].goal_b; landmark colours [0.65,0.15,0.15],[0.15,0.65,0.15],[0.15,0.15,0.65] (:44-46) */
+static void observe_speaker_listener(const mpe_desc *d, const real *pv, const real *lm, const real *comm,
+                                     const int32_t *goal, real *obs, real *rew) {
+    const int L = d->n_landmarks, C = d->dim_c, g = goal[0];
+    real *o = obs;
+    for (int c = 0; c < 3; ++c) *o++ = (c == g) ? R(0.65) : R(0.15);        /* speaker: goal_color :70-72,87-88 */
+    *o++ = VX(1); *o++ = VY(1);                                             /* listener :90-92 */
+    for (int l = 0; l < L; ++l) { *o++ = LX(l) - PX(1); *o++ = LY(l) - PY(1); }
+    for (int q = 0; q < C; ++q) *o++ = comm[0 * C + q];
+    real dx = PX(1) - LX(g), dy = PY(1) - LY(g);                            /* reward :63-67: a = agents[0] */
+    rew[0] = rew[1] = -(dx * dx + dy * dy);
+}
+
+/* ---- simple_reference.py ----------------------------------------------------------------- */
+/* goal[i] = agents[i].goal_b; agents[i].goal_a = the other agent; landmark colours (:37-39) */
+static void observe_reference(const mpe_desc *d, const real *pv, const real *lm, const real *comm,
+                              const int32_t *goal, real *obs, real *rew) {
+    const int A = d->n_agents, L = d->n_landmarks, C = d->dim_c;
+    real *o = obs;
+    for (int i = 0; i < A; ++i) {
+        const int other = 1 - i, g = goal[i];
+        *o++ = VX(i); *o++ = VY(i);                                         /* :80 */
+        for (int l = 0; l < L; ++l) { *o++ = LX(l) - PX(i); *o++ = LY(l) - PY(i); }
+        for (int c = 0; c < 3; ++c) *o++ = (c == g) ? R(0.75) : R(0.25);    /* goal_color[1] = goal_b.color :64-66 */
+        for (int q = 0; q < C; ++q) *o++ = comm[other * C + q];             /* :76-79 */
+        real dx = PX(other) - LX(g), dy = PY(other) - LY(g);                /* reward :55-59 */
+        rew[i] = -(dx * dx + dy * dy);
+    }
+}
+
+/* ---- simple_crypto.py -------------------------------------------------------------------- */
+/* goal[0] = goal landmark, goal[1] = key landmark; colours are one-hot in dim_c (:58-62) */
+static void observe_crypto(const mpe_desc *d, const real *comm, const int32_t *goal, real *obs, real *rew, real *info) {
+    const int A = d->n_agents, C = d->dim_c, g = goal[0], key = goal[1], I = 2 * C;
+    real *o = obs;
+    real err[MAXA];
+    int spoke[MAXA];
+    for (int a = 0; a < A; ++a) {
+        real e = 0;
+        int nz = 0;
+        for (int q = 0; q < C; ++q) {
+            real df = comm[a * C + q] - (q == g ? R(1.0) : R(0.0));
+            e += df * df;
+            if (comm[a * C + q] != 0) nz = 1;
+        }
+        err[a] = e; spoke[a] = nz;
+    }
+    for (int i = 0; i < A; ++i) {
+        const int speaker = (i == 2);
+        if (speaker) {                                                      /* :157-162 */
+            for (int q = 0; q < C; ++q) *o++ = (q == g) ? R(1.0) : R(0.0);
+            for (int q = 0; q < C; ++q) *o++ = (q == key) ? R(1.0) : R(0.0);
+        } else if (!d->agent_adversary[i]) {                                /* listener :163-168 */
+            for (int q = 0; q < C; ++q) *o++ = (q == key) ? R(1.0) : R(0.0);
+            for (int q = 0; q < C; ++q) *o++ = comm[2 * C + q];
+        } else {                                                            /* adversary :169-174 */
+            for (int q = 0; q < C; ++q) *o++ = comm[2 * C + q];
+        }
+        real r = 0;
+        if (d->agent_adversary[i]) {                                        /* adversary_reward :115-121 */
+            if (spoke[i]) r -= err[i];
+        } else {                                                            /* agent_reward :94-113 */
+            real good_rew = 0, adv_rew = 0;
+            for (int a = 0; a < A; ++a) if (!d->agent_adversary[a] && a != 2 && spoke[a]) good_rew -= err[a];
+            for (int a = 0; a < A; ++a) if (d->agent_adversary[a] && spoke[a]) adv_rew += err[a];
+            r = adv_rew + good_rew;
+        }
+        rew[i] = r;
+        if (info) {                                                         /* benchmark_data :66-67 */
+            for (int q = 0; q < C; ++q) info[i * I + q] = comm[i * C + q];
+            for (int q = 0; q < C; ++q) info[i * I + C + q] = (q == g) ? R(1.0) : R(0.0);
+        }
+    }
+}
+
 static void observe_world(const mpe_desc *d, const real *pv, const real *lm, const real *comm,
                           const int32_t *goal, real *obs, real *rew, uint8_t *done, real *info,
                           uint32_t flags) {
-    (void)goal;
     const int A = d->n_agents;
     switch (d->scenario) {
     case MPE_SCN_SIMPLE: observe_simple(d, pv, lm, obs, rew); break;
     case MPE_SCN_SPREAD: observe_spread(d, pv, lm, comm, obs, rew, info); break;
     case MPE_SCN_TAG: observe_tag(d, pv, lm, obs, rew, info); break;
     case MPE_SCN_WORLD_COMM: observe_world_comm(d, pv, lm, comm, obs, rew, info); break;
+    case MPE_SCN_ADVERSARY: observe_adversary(d, pv, lm, goal, obs, rew, info); break;
+    case MPE_SCN_PUSH: observe_push(d, pv, lm, goal, obs, rew); break;
+    case MPE_SCN_SPEAKER_LISTENER: observe_speaker_listener(d, pv, lm, comm, goal, obs, rew); break;
+    case MPE_SCN_REFERENCE: observe_reference(d, pv, lm, comm, goal, obs, rew); break;
+    case MPE_SCN_CRYPTO: observe_crypto(d, comm, goal, obs, rew, info); break;
     default: break;
     }
     /* MultiAgentEnv.step glue (environment.py:95,100-102): done_callback is None -> False;

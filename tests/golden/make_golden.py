@@ -23,12 +23,22 @@ sys.path.insert(0, os.path.join(HERE, "..", "..", "oracle"))
 import refshim  # noqa: E402
 
 CONFIGS = [
+    ("simple_adversary", None, 12, 25),
+    ("simple_push", None, 12, 25),
+    ("simple_speaker_listener", None, 12, 25),
+    ("simple_reference", None, 12, 25),
+    ("simple_crypto", None, 12, 25),
     ("simple", None, 16, 25),
     ("simple_spread", 3, 16, 25),
     ("simple_spread", 6, 12, 25),
     ("simple_tag", None, 16, 25),
     ("simple_world_comm", None, 12, 25),
 ]
+
+
+SEEDS = {"simple": 1, "simple_spread_n3": 2, "simple_spread_n6": 3, "simple_tag": 4, "simple_world_comm": 5,
+         "simple_adversary": 11, "simple_push": 12, "simple_speaker_listener": 13, "simple_reference": 14,
+         "simple_crypto": 15}
 
 
 def act_dim(space):
@@ -60,21 +70,37 @@ def snapshot(world):
     return pv, comm
 
 
+def goals_of(name, world):
+    """per-world goal indices chosen by reset_world (np.random.choice(world.landmarks))"""
+    lms = world.landmarks
+    idx = lambda e: [i for i, l in enumerate(lms) if l is e][0]  # noqa: E731
+    if name in ("simple_adversary", "simple_push"):
+        return [idx(world.agents[0].goal_a)]
+    if name == "simple_speaker_listener":
+        return [idx(world.agents[0].goal_b)]
+    if name == "simple_reference":
+        return [idx(world.agents[0].goal_b), idx(world.agents[1].goal_b)]
+    if name == "simple_crypto":
+        return [idx(world.agents[0].goal_a), int(np.argmax(world.agents[2].key))]
+    return []
+
+
 def flatten_info(name, info_n):
     out = []
     for item in info_n["n"]:
         if isinstance(item, dict):
             out.append([])
         elif isinstance(item, tuple):
-            out.append([float(v) for v in item])
+            out.append([float(v) for part in item for v in np.atleast_1d(part)])
         else:
             out.append([float(item)])
-    return np.array(out, dtype=np.float64)
+    width = max(len(r) for r in out)
+    return np.array([r + [0.0] * (width - len(r)) for r in out], dtype=np.float64)   # ragged rows zero-padded
 
 
 def run_config(name, n, W, T, seed, force_discrete=False):
     rng = np.random.RandomState(seed)
-    rec = dict(pv0=[], lm=[], comm0=[], act=[], pv=[], comm=[], obs=[], rew=[], done=[], info=[])
+    rec = dict(pv0=[], lm=[], comm0=[], goal=[], act=[], pv=[], comm=[], obs=[], rew=[], done=[], info=[])
     props = None
     for w in range(W):
         np.random.seed(seed * 1000 + w)
@@ -99,6 +125,7 @@ def run_config(name, n, W, T, seed, force_discrete=False):
             for a in world.agents:
                 a.state.p_pos = rng.uniform(-0.12, 0.12, 2)
         pv0, comm0 = snapshot(world)
+        rec["goal"].append(np.array(goals_of(name, world), dtype=np.int32))
         rec["pv0"].append(pv0)
         rec["comm0"].append(comm0)
         rec["lm"].append(np.array([l.state.p_pos for l in world.landmarks]))
@@ -109,10 +136,13 @@ def run_config(name, n, W, T, seed, force_discrete=False):
             acts = []
             for i, sp in enumerate(env.action_space):
                 d = act_dim(sp)
-                logits = temperature * rng.randn(d)
-                logits[:5] += 2.0 * drift[i] if mode in (2, 3) else 0.0
-                p = np.exp(logits[:5] - logits[:5].max())
-                a = np.concatenate([p / p.sum(), rng.uniform(0, 1, d - 5)]) if d > 5 else p / p.sum()
+                if not world.agents[i].movable:          # speaker-only agents: the comm chunk
+                    a = rng.uniform(0, 1, d) * (rng.uniform() > 0.15)   # sometimes an all-zero utterance
+                else:
+                    logits = temperature * rng.randn(5)
+                    logits += 2.0 * drift[i] if mode in (2, 3) else 0.0
+                    p = np.exp(logits - logits.max())
+                    a = np.concatenate([p / p.sum(), rng.uniform(0, 1, d - 5)]) if d > 5 else p / p.sum()
                 acts.append(a)
             obs_n, rew_n, done_n, info_n = env.step([a.copy() for a in acts])
             pv, comm = snapshot(world)
@@ -161,11 +191,16 @@ def kat():
 
 
 def main():
+    only = sys.argv[1:]
     for idx, (name, n, W, T) in enumerate(CONFIGS):
+        if only and name not in only:
+            continue
         tag = name + ("_n%d" % n if n else "")
-        data = run_config(name, n, W, T, seed=idx + 1)
+        data = run_config(name, n, W, T, seed=SEEDS[tag])
         np.savez_compressed(os.path.join(HERE, tag + ".npz"), **data)
         print(tag, {k: v.shape for k, v in data.items() if not k.startswith("prop_")})
+    if only:
+        return
     data = run_config("simple_tag", None, 8, 10, seed=77, force_discrete=True)
     np.savez_compressed(os.path.join(HERE, "simple_tag_force_discrete.npz"), **data)
     np.savez_compressed(os.path.join(HERE, "kat.npz"), **kat())

@@ -12,7 +12,13 @@ CONFIGS = {
     "simple_spread_n6": ("simple_spread", {"num_agents": 6}),
     "simple_tag": ("simple_tag", {}),
     "simple_world_comm": ("simple_world_comm", {}),
+    "simple_adversary": ("simple_adversary", {}),
+    "simple_push": ("simple_push", {}),
+    "simple_speaker_listener": ("simple_speaker_listener", {}),
+    "simple_reference": ("simple_reference", {}),
+    "simple_crypto": ("simple_crypto", {}),
 }
+NO_BENCHMARK = ("simple", "simple_push", "simple_speaker_listener", "simple_reference")
 
 
 def load_golden(tag):
@@ -23,11 +29,13 @@ def make_product_env(tag, **kw):
     from multiagent_particle_envs_b200 import make_env
     name, skw = CONFIGS[tag]
     kw.update(skw)
-    return make_env(name, benchmark=(name != "simple"), **kw)
+    return make_env(name, benchmark=(name not in NO_BENCHMARK), **kw)
 
 
 def descriptor(tag):
-    return make_product_env(tag).world.descriptor()
+    from multiagent_particle_envs_b200 import scenarios
+    name, kw = CONFIGS[tag]
+    return scenarios.load(name).Scenario(**kw).make_world().descriptor()
 
 
 def step_flags(tag_or_golden):
@@ -59,20 +67,29 @@ def random_states(desc, n, rng, mode="mixed"):
     comm = np.zeros((n, A, C))
     for i in range(A):
         if not desc.agent_silent[i]:
-            comm[:, i, :] = rng.uniform(0, 1, (n, C))
+            comm[:, i, :] = rng.uniform(0, 1, (n, C)) * (rng.uniform(0, 1, (n, 1)) > 0.1)
+        if not desc.agent_movable[i]:
+            pv[:, i, 2:4] = 0.0
     return pv, lm, comm
 
 
-def random_actions(act_dims, n, rng, temperature=2.0):
+def random_goals(n_goals, n_landmarks, n, rng):
+    return rng.randint(0, max(n_landmarks, 1), (n, n_goals)).astype(np.int32)
+
+
+def random_actions(act_dims, n, rng, temperature=2.0, movable=None):
     """probability vectors as MADDPG emits (softmax of logits) + uniform comm"""
     parts = []
-    for d in act_dims:
-        logits = temperature * rng.randn(n, 5)
-        p = np.exp(logits - logits.max(axis=1, keepdims=True))
-        p /= p.sum(axis=1, keepdims=True)
-        parts.append(p)
-        if d > 5:
-            parts.append(rng.uniform(0, 1, (n, d - 5)))
+    for i, d in enumerate(act_dims):
+        mov = True if movable is None else bool(movable[i])
+        if mov:
+            logits = temperature * rng.randn(n, 5)
+            p = np.exp(logits - logits.max(axis=1, keepdims=True))
+            p /= p.sum(axis=1, keepdims=True)
+            parts.append(p)
+            d -= 5
+        if d > 0:
+            parts.append(rng.uniform(0, 1, (n, d)) * (rng.uniform(0, 1, (n, 1)) > 0.1))
     return np.concatenate(parts, axis=1)
 
 

@@ -36,7 +36,13 @@ SHAPES = {
     "simple_spread_n6": (6, [5] * 6, [36] * 6, 1254),
     "simple_tag": (4, [5] * 4, [16, 16, 16, 14], 492),
     "simple_world_comm": (6, [9, 5, 5, 5, 5, 5], [34, 34, 34, 34, 28, 28], 1182),
+    "simple_adversary": (3, [5, 5, 5], [8, 10, 10], None),
+    "simple_push": (2, [5, 5], [8, 19], None),
+    "simple_speaker_listener": (2, [3, 5], [3, 11], None),
+    "simple_reference": (2, [15, 15], [21, 21], None),
+    "simple_crypto": (3, [4, 4, 4], [4, 8, 8], None),
 }
+N_GOALS = {"simple_adversary": 1, "simple_push": 1, "simple_speaker_listener": 1, "simple_reference": 2, "simple_crypto": 2}
 
 
 @pytest.mark.parametrize("tag", list(CONFIGS))
@@ -49,12 +55,17 @@ def test_shapes_spaces_and_descriptor(tag):
     assert [s.shape for s in env.observation_space] == [(d,) for d in obs] == [(int(d),) for d in g["prop_obs_dims"]]
     sh = env.world.native_shapes()
     assert sh.act_dims == act == [int(d) for d in g["prop_act_dims"]]
-    assert sh.bytes_per_env_step == nbytes
+    A, L, C = n, len(g["prop_landmark_size"]), int(g["prop_dim_c"])
+    mov, sil = list(g["prop_agent_movable"]), list(g["prop_agent_silent"])
+    formula = 4 * (4 * A + 2 * L + N_GOALS.get(tag, 0) + sum(act) + 4 * sum(mov) + sum(obs) + A
+                   + C * sum(1 - x for x in sil)) + A        # SURVEY.md 8(d), compulsory traffic
+    assert sh.bytes_per_env_step == formula and (nbytes is None or nbytes == formula)
+    assert sh.n_goals == N_GOALS.get(tag, 0)
     for i, sp in enumerate(env.action_space):
-        if act[i] == 5:
-            assert sp.n == 5
+        if mov[i] and not sil[i]:
+            assert isinstance(sp, MultiDiscrete) and list(sp.high - sp.low + 1) == [5, C]
         else:
-            assert isinstance(sp, MultiDiscrete) and list(sp.high - sp.low + 1) == [5, 4]
+            assert sp.n == (5 if mov[i] else C)
     assert env.shared_reward == bool(int(g["prop_shared_reward"]))
     assert env.discrete_action_space is True and env.discrete_action_input is False and env.time == 0
     d = env.world.descriptor()

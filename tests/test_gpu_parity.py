@@ -6,7 +6,8 @@ on the kernels' own stored state.  Run on the B200 box: pytest -m gpu."""
 import numpy as np
 import pytest
 
-from helpers import CONFIGS, load_golden, make_product_env, random_actions, random_states, split_cols, step_flags
+from helpers import (CONFIGS, load_golden, make_product_env, random_actions, random_goals, random_states, split_cols,
+                     step_flags)
 
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
@@ -15,9 +16,11 @@ RTOL, ATOL = 1e-5, 1e-6
 TAGS = list(CONFIGS)
 
 
-def inject(nw, pv, lm, comm):
-    """oracle layout [n,A,4] / [n,L,2] / [n,A,C] -> the SoA device tensors"""
+def inject(nw, pv, lm, comm, goal=None):
+    """oracle layout [n,A,4] / [n,L,2] / [n,A,C] / [n,G] -> the SoA device tensors"""
     dev = nw.device
+    if goal is not None and nw.n_goals:
+        nw.goal.copy_(torch.as_tensor(np.ascontiguousarray(goal), dtype=torch.int32, device=dev).t())
     nw.agent_pv.copy_(torch.as_tensor(pv, dtype=torch.float32, device=dev).permute(1, 0, 2))
     if nw.n_landmarks:
         nw.lm_p.copy_(torch.as_tensor(lm, dtype=torch.float32, device=dev).permute(1, 0, 2))
@@ -65,7 +68,8 @@ def test_golden_fixtures_single_step(tag):
     env.reset()
     nw = env.world.native
     for t in range(T):
-        inject(nw, g["pv0"] if t == 0 else g["pv"][:, t - 1], g["lm"], g["comm0"] if t == 0 else g["comm"][:, t - 1])
+        inject(nw, g["pv0"] if t == 0 else g["pv"][:, t - 1], g["lm"], g["comm0"] if t == 0 else g["comm"][:, t - 1],
+               g.get("goal"))
         obs, rew, done, info = gpu_step(env, g["act"][:, t])
         pv, comm = extract(nw)
         np.testing.assert_allclose(pv, g["pv"][:, t], rtol=RTOL, atol=ATOL)
@@ -87,7 +91,7 @@ def test_golden_fixtures_free_running(tag):
     env = make_product_env(tag, num_envs=W)
     env.reset()
     nw = env.world.native
-    inject(nw, g["pv0"], g["lm"], g["comm0"])
+    inject(nw, g["pv0"], g["lm"], g["comm0"], g.get("goal"))
     for t in range(T):
         obs, rew, done, info = gpu_step(env, g["act"][:, t])
     pv, _ = extract(nw)
@@ -96,7 +100,9 @@ def test_golden_fixtures_free_running(tag):
 
 
 @pytest.mark.parametrize("tag,n", [("simple", 4096), ("simple_spread_n3", 8192), ("simple_spread_n6", 4096),
-                                   ("simple_tag", 8192), ("simple_world_comm", 4096)])
+                                   ("simple_tag", 8192), ("simple_world_comm", 4096), ("simple_adversary", 4096),
+                                   ("simple_push", 4096), ("simple_speaker_listener", 4096), ("simple_reference", 4096),
+                                   ("simple_crypto", 4096)])
 def test_seeded_worlds_vs_oracle(tag, n):
     from oracle import Oracle
     from multiagent_particle_envs_b200 import _lib
@@ -109,12 +115,14 @@ def test_seeded_worlds_vs_oracle(tag, n):
     rng = np.random.RandomState(1234)
     pv0, lm, comm0 = random_states(desc, n, rng)
     pv0, lm, comm0 = pv0.astype(np.float32), lm.astype(np.float32), comm0.astype(np.float32)
-    act = random_actions(nw.act_dims, n, rng).astype(np.float32)
-    inject(nw, pv0, lm, comm0)
+    movable = [bool(desc.agent_movable[i]) for i in range(desc.n_agents)]
+    act = random_actions(nw.act_dims, n, rng, movable=movable).astype(np.float32)
+    goal = random_goals(nw.n_goals, desc.n_landmarks, n, rng) if nw.n_goals else None
+    inject(nw, pv0, lm, comm0, goal)
     obs, rew, done, info = gpu_step(env, act)
     pv, comm = extract(nw)
     # (1) against the reference arithmetic (fp64) on identical fp32 inputs
-    rpv, rcomm, robs, rrew, rdone, rinfo = o64.step(pv0, lm, comm0, act, flags)
+    rpv, rcomm, robs, rrew, rdone, rinfo = o64.step(pv0, lm, comm0, act, flags, goal=goal)
     np.testing.assert_allclose(pv, rpv, rtol=RTOL, atol=ATOL)
     np.testing.assert_allclose(comm, rcomm, rtol=1e-7, atol=0)
     np.testing.assert_allclose(obs, robs, rtol=RTOL, atol=ATOL)
@@ -122,16 +130,17 @@ def test_seeded_worlds_vs_oracle(tag, n):
     assert np.isclose(rew, rrew, rtol=RTOL, atol=5e-6).mean() > 0.995
     # (2) flags: the fp32 oracle evaluated on the kernel's OWN stored post-step state must give
     # bit-identical observations, contact counts and done masks
-    fobs, frew, fdone, finfo = o32.observe(pv, lm, comm, flags)
+    fobs, frew, fdone, finfo = o32.observe(pv, lm, comm, flags, goal=goal)
     assert np.array_equal(obs, fobs)
     assert np.array_equal(done, fdone)
-    count_cols = [1, 3] if tag.startswith("simple_spread") else ([0] if info.shape[2] else [])
+    count_cols = [1, 3] if tag.startswith("simple_spread") else ([0] if tag in ("simple_tag", "simple_world_comm") else [])
     for c in count_cols:                                              # collisions / occupied landmarks
         assert np.array_equal(info[:, :, c], finfo[:, :, c])
     np.testing.assert_allclose(rew, frew, rtol=2e-6, atol=2e-6)       # only expf ulps may differ
     # some worlds really are in contact, otherwise the test proves little
-    if desc.n_agents > 1:
-        assert (np.abs(rpv[:, :, 2:4] - pv0[:, :, 2:4] * 0.75).max(axis=(1, 2)) > 1.0).mean() > 0.05
+    if any(desc.agent_collide[i] for i in range(desc.n_agents)) and desc.n_agents > 1:
+        floor = 0.003 if tag == "simple_push" else 0.05            # two small agents rarely touch
+        assert (np.abs(rpv[:, :, 2:4] - pv0[:, :, 2:4] * 0.75).max(axis=(1, 2)) > 1.0).mean() > floor
 
 
 @pytest.mark.parametrize("tag", TAGS)
@@ -147,9 +156,11 @@ def test_fused_step_equals_three_kernel_path(tag):
     desc = env_a.world.descriptor()
     rng = np.random.RandomState(7)
     pv0, lm, comm0 = random_states(desc, n, rng)
-    act = random_actions(na.act_dims, n, rng).astype(np.float32)
-    inject(na, pv0, lm, comm0)
-    inject(nb, pv0, lm, comm0)
+    movable = [bool(desc.agent_movable[i]) for i in range(desc.n_agents)]
+    act = random_actions(na.act_dims, n, rng, movable=movable).astype(np.float32)
+    goal = random_goals(na.n_goals, desc.n_landmarks, n, rng) if na.n_goals else None
+    inject(na, pv0, lm, comm0, goal)
+    inject(nb, pv0, lm, comm0, goal)
     obs, rew, done, info = gpu_step(env_a, act)
     acts = [torch.as_tensor(np.ascontiguousarray(a), device=nb.device) for a in split_cols(act, nb.act_dims)]
     flags = _lib.FLAG_SHARED_REWARD if env_b.shared_reward else 0
