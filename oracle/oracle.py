@@ -68,7 +68,11 @@ class Oracle(object):
         pv = self._arr(pv, (n, self.A, 4)).copy()
         lm = self._arr(lm, (n, self.L, 2))
         comm = self._arr(comm, (n, self.A, self.C)).copy()
-        act = self._arr(act, (n, sum(self.act_dims)))
+        width = sum(self.act_dims)
+        if flags & 4:   # MPE_FLAG_DISCRETE_ACTION_INPUT: one integer per sub-action
+            d = self.desc
+            width = sum((1 if d.agent_movable[i] else 0) + (0 if d.agent_silent[i] else 1) for i in range(self.A))
+        act = self._arr(act, (n, width))
         obs, rew, done, info = self.empty_outputs(n)
         g = np.ascontiguousarray(goal, np.int32) if goal is not None else None
         fn = self._f("mpe_oracle_step")
