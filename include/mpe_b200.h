@@ -170,7 +170,11 @@ MPE_API int mpe_step(mpe_handle h, void *agent_pv_dev, const void *lm_p_dev, flo
 /* Same step for a caller that holds HOST buffers (what the reference's callers hold):
  * act_n_host[i] -> (async H2D into act_n_dev[i]) -> mpe_step -> (async D2H) obs_n_host[i],
  * rew_host, done_host, all ordered on `stream`.  Host buffers should be pinned for the copies
- * to be asynchronous.  The caller synchronises the stream before reading the outputs. */
+ * to be asynchronous.  The caller synchronises the stream before reading the outputs.
+ * Large batches are cut into MPE_B200_HOST_CHUNKS (default 4) world ranges that alternate
+ * between two library-owned streams forked from / joined to `stream`, so that the upload + step of one range
+ * overlaps the download of the previous one (full-duplex PCIe).  Pipelining starts at MPE_B200_HOST_CHUNK_MIN worlds (default 262144: below that the
+ * extra copy calls cost more than the overlap gains on PCIe Gen5). */
 MPE_API int mpe_step_host(mpe_handle h, void *agent_pv_dev, const void *lm_p_dev, float *comm_dev,
                   const int32_t *goal_dev, const float *const *act_n_host, float *const *act_n_dev,
                   float *const *obs_n_dev, float *rew_dev, uint8_t *done_dev, float *info_dev,

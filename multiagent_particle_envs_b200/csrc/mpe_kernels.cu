@@ -130,13 +130,14 @@ __global__ void __launch_bounds__(kMaxThreads) mpe_kernel(const __grid_constant_
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t n = a.n;
-    const int64_t w0 = (static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + warp) * 32;
+    const int64_t end = a.begin + a.count;
+    const int64_t w0 = a.begin + (static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + warp) * 32;
     // Programmatic dependent launch (opt-in, MPE_B200_PDL=1): touch no global memory before the
     // previous grid has completed and flushed; the next grid is released late (before our stores).
     if (a.flags & kFlagPdlEarly) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (w0 >= n) return;  // whole warp exits together
-    const int rows = (n - w0) < 32 ? static_cast<int>(n - w0) : 32;
+    if (w0 >= end) return;  // whole warp exits together
+    const int rows = (end - w0) < 32 ? static_cast<int>(end - w0) : 32;
     const bool active = lane < rows;
     const int64_t wi = w0 + (active ? lane : 0);  // inactive lanes shadow row 0 and never store
     float *s_warp = smem + warp * Shape<P>::kWarpFloats;
@@ -431,6 +432,10 @@ struct mpe_env {
     const Program *prog;
     int64_t n;
     int device;
+    // mpe_step_host pipelines chunks of the batch over two internal streams so that the H2D copy of one
+    // chunk overlaps the D2H copy of the previous one (PCIe is full duplex)
+    cudaStream_t aux[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
 };
 
 static thread_local char g_cuda_err[256] = "";
@@ -484,6 +489,19 @@ extern "C" int mpe_create(const mpe_desc *desc, int64_t n_env, int device, mpe_h
 
     mpe_env *h = new (std::nothrow) mpe_env();
     if (!h) return MPE_ERR_BAD_ARG;
+    if (device != -1) {
+        int prev = 0;
+        cudaGetDevice(&prev);
+        cudaSetDevice(device);
+        cudaError_t e = cudaSuccess;
+        for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+            e = cudaStreamCreateWithFlags(&h->aux[k], cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join[k], cudaEventDisableTiming);
+        }
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+        cudaSetDevice(prev);
+        if (e != cudaSuccess) { delete h; return cuda_fail(e, "mpe_create: streams/events"); }
+    }
     h->desc = *desc;
     h->prog = prog;
     h->n = n_env;
@@ -513,6 +531,11 @@ extern "C" int mpe_create(const mpe_desc *desc, int64_t n_env, int device, mpe_h
 
 extern "C" int mpe_destroy(mpe_handle h) {
     if (!h) return MPE_ERR_BAD_ARG;
+    for (int k = 0; k < 2; ++k) {
+        if (h->aux[k]) cudaStreamDestroy(h->aux[k]);
+        if (h->ev_join[k]) cudaEventDestroy(h->ev_join[k]);
+    }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     delete h;
     return MPE_OK;
 }
@@ -540,14 +563,18 @@ static int pdl_mode() {  // 0 = off (default), 1 = late trigger, 2 = early trigg
     return m;
 }
 
-static int launch(mpe_handle h, int mode, StepArgs &args, void *stream) {
+static int launch(mpe_handle h, int mode, StepArgs &args, void *stream, int64_t begin = 0, int64_t count = -1) {
     if (h->device < 0) return MPE_ERR_NO_DEVICE;
     args.d = h->dev;
     args.n = h->n;
-    const int64_t warps = (h->n + 31) / 32;
-    // Warps are autonomous, so the block size only sets scheduling granularity: small batches use
-    // one warp per block so that the (few) blocks spread evenly over the 148 SMs.
-    const int wpb = warps <= 148 * 32 ? 1 : (warps <= 148 * 64 ? 2 : kMaxWarpsPerBlock);
+    args.begin = begin;
+    args.count = count < 0 ? h->n - begin : count;
+    const int64_t warps = (args.count + 31) / 32;
+    // Warps are autonomous, so the block size only sets scheduling granularity (measured at 65536 worlds:
+    // 1 / 2 / 4 warps per block = 6.69 / 6.34 / 7.06 us per step): tiny batches use one warp per block so
+    // that the few blocks spread over all 148 SMs, mid-size batches two, large ones four.
+    static const int wpb_env = [] { const char *e = getenv("MPE_B200_WPB"); int v = e ? atoi(e) : 0; return (v == 1 || v == 2 || v == 4) ? v : 0; }();
+    const int wpb = wpb_env ? wpb_env : (warps <= 148 * 4 ? 1 : (warps <= 148 * 64 ? 2 : kMaxWarpsPerBlock));
     const int64_t blocks = (warps + wpb - 1) / wpb;
     if (blocks > 0x7fffffffLL) return MPE_ERR_BAD_ARG;
     int prev = 0;
@@ -682,42 +709,112 @@ static int issue_copies(CopySeg *seg, int n, cudaMemcpyKind kind, cudaStream_t s
     return MPE_OK;
 }
 
+static int step_range(mpe_handle h, void *pv, const void *lm, float *comm, const int32_t *goal,
+                      const float *const *act_n, float *const *obs_n, float *rew, uint8_t *done, float *info,
+                      uint32_t flags, void *stream, int64_t begin, int64_t count) {
+    StepArgs a{};
+    int r = fill_state(h, a, pv, lm, comm, goal);
+    if (r) return r;
+    r = fill_actions(h, a, act_n);
+    if (r) return r;
+    r = fill_outputs(h, a, obs_n, rew, done, info);
+    if (r) return r;
+    a.flags = flags;
+    return launch(h, kFusedStep, a, stream, begin, count);
+}
+
+static int64_t host_chunk_min() {  // MPE_B200_HOST_CHUNK_MIN: smallest batch that is pipelined (default 262144)
+    static const int64_t m = [] { const char *e = getenv("MPE_B200_HOST_CHUNK_MIN"); return e ? atoll(e) : 262144LL; }();
+    return m;
+}
+static int host_chunks() {  // MPE_B200_HOST_CHUNKS: 1 disables the pipeline (default 4)
+    static const int c = [] { const char *e = getenv("MPE_B200_HOST_CHUNKS"); int v = e ? atoi(e) : 4; return v < 1 ? 1 : (v > 16 ? 16 : v); }();
+    return c;
+}
+
 extern "C" int mpe_step_host(mpe_handle h, void *pv, const void *lm, float *comm, const int32_t *goal,
                              const float *const *act_n_host, float *const *act_n_dev, float *const *obs_n_dev,
                              float *rew_dev, uint8_t *done_dev, float *info_dev, float *const *obs_n_host,
                              float *rew_host, uint8_t *done_host, float *info_host, uint32_t flags, void *stream) {
     if (!h || !act_n_host || !act_n_dev || !obs_n_host || !obs_n_dev || !rew_host || !done_host) return MPE_ERR_BAD_ARG;
     if (h->device < 0) return MPE_ERR_NO_DEVICE;
+    if (flags & MPE_FLAG_DISCRETE_ACTION_INPUT) return MPE_ERR_UNSUPPORTED;
     const Program *p = h->prog;
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaStream_t user = static_cast<cudaStream_t>(stream);
     const size_t n = static_cast<size_t>(h->n);
-    CopySeg seg[kMaxA + 3];
-    int ns = 0;
-    for (int i = 0; i < p->A; ++i) {
+    for (int i = 0; i < p->A; ++i)
         if (!act_n_host[i] || !act_n_dev[i] || !obs_n_host[i] || !obs_n_dev[i]) return MPE_ERR_BAD_ARG;
-        seg[ns++] = {reinterpret_cast<char *>(act_n_dev[i]), reinterpret_cast<const char *>(act_n_host[i]),
-                     sizeof(float) * n * p->act_dim[i]};
-    }
+    const bool want_info = info_host && info_dev && p->INFO > 0;
     int prev = 0;
     CUDA_TRY(cudaGetDevice(&prev));
     if (prev != h->device) CUDA_TRY(cudaSetDevice(h->device));
-    int rc = issue_copies(seg, ns, cudaMemcpyHostToDevice, s, "cudaMemcpyAsync(H2D actions)", false);
-    const bool want_info = info_host && info_dev && p->INFO > 0;
-    if (rc == MPE_OK)
-        rc = mpe_step(h, pv, lm, comm, goal, act_n_dev, obs_n_dev, rew_dev, done_dev, want_info ? info_dev : nullptr,
-                      flags, stream);
-    if (rc == MPE_OK) {
-        ns = 0;
+    int rc = MPE_OK;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(user, &cap);
+    // measured on B200 (PCIe Gen5): below ~256k worlds the extra copy calls cost more than the overlap gains
+    const int chunks = (h->n >= host_chunk_min() && cap == cudaStreamCaptureStatusNone) ? host_chunks() : 1;
+    if (chunks == 1) {
+        // small batches: one H2D per agent, one launch, one coalesced D2H
+        CopySeg seg[kMaxA + 3];
+        int ns = 0;
         for (int i = 0; i < p->A; ++i)
-            seg[ns++] = {reinterpret_cast<char *>(obs_n_host[i]), reinterpret_cast<const char *>(obs_n_dev[i]),
-                         sizeof(float) * n * p->obs_dim[i]};
-        seg[ns++] = {reinterpret_cast<char *>(rew_host), reinterpret_cast<const char *>(rew_dev), sizeof(float) * n * p->A};
-        seg[ns++] = {reinterpret_cast<char *>(done_host), reinterpret_cast<const char *>(done_dev), n * p->A};
-        if (want_info)
-            seg[ns++] = {reinterpret_cast<char *>(info_host), reinterpret_cast<const char *>(info_dev),
-                         sizeof(float) * n * p->A * p->INFO};
-        rc = issue_copies(seg, ns, cudaMemcpyDeviceToHost, s, "cudaMemcpyAsync(D2H obs/rew/done/info)",
-                          (flags & MPE_FLAG_HOST_SLAB) != 0);
+            seg[ns++] = {reinterpret_cast<char *>(act_n_dev[i]), reinterpret_cast<const char *>(act_n_host[i]),
+                         sizeof(float) * n * p->act_dim[i]};
+        rc = issue_copies(seg, ns, cudaMemcpyHostToDevice, user, "cudaMemcpyAsync(H2D actions)", false);
+        if (rc == MPE_OK)
+            rc = step_range(h, pv, lm, comm, goal, act_n_dev, obs_n_dev, rew_dev, done_dev, want_info ? info_dev : nullptr,
+                            flags, stream, 0, h->n);
+        if (rc == MPE_OK) {
+            ns = 0;
+            for (int i = 0; i < p->A; ++i)
+                seg[ns++] = {reinterpret_cast<char *>(obs_n_host[i]), reinterpret_cast<const char *>(obs_n_dev[i]),
+                             sizeof(float) * n * p->obs_dim[i]};
+            seg[ns++] = {reinterpret_cast<char *>(rew_host), reinterpret_cast<const char *>(rew_dev), sizeof(float) * n * p->A};
+            seg[ns++] = {reinterpret_cast<char *>(done_host), reinterpret_cast<const char *>(done_dev), n * p->A};
+            if (want_info)
+                seg[ns++] = {reinterpret_cast<char *>(info_host), reinterpret_cast<const char *>(info_dev),
+                             sizeof(float) * n * p->A * p->INFO};
+            rc = issue_copies(seg, ns, cudaMemcpyDeviceToHost, user, "cudaMemcpyAsync(D2H obs/rew/done/info)",
+                              (flags & MPE_FLAG_HOST_SLAB) != 0);
+        }
+    } else {
+        // Large batches: the worlds are cut into `chunks` ranges (multiples of 128 worlds, so every tile stays
+        // 16-byte aligned) that alternate between two internal streams: while chunk c drains over the D2H copy
+        // engine, chunk c+1 uploads its actions and computes.  The caller's stream forks into and joins the two.
+        cudaError_t e = cudaEventRecord(h->ev_fork, user);
+        for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaStreamWaitEvent(h->aux[k], h->ev_fork, 0);
+        if (e != cudaSuccess) rc = cuda_fail(e, "mpe_step_host: fork");
+        const int64_t per = ((h->n + chunks - 1) / chunks + 127) / 128 * 128;
+        for (int c = 0; c < chunks && rc == MPE_OK; ++c) {
+            const int64_t begin = c * per;
+            if (begin >= h->n) break;
+            const int64_t count = (begin + per <= h->n) ? per : h->n - begin;
+            cudaStream_t s = h->aux[c & 1];
+            for (int i = 0; i < p->A && e == cudaSuccess; ++i)
+                e = cudaMemcpyAsync(act_n_dev[i] + begin * p->act_dim[i], act_n_host[i] + begin * p->act_dim[i],
+                                    sizeof(float) * count * p->act_dim[i], cudaMemcpyHostToDevice, s);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemcpyAsync(H2D actions)"); break; }
+            rc = step_range(h, pv, lm, comm, goal, act_n_dev, obs_n_dev, rew_dev, done_dev, want_info ? info_dev : nullptr,
+                            flags, s, begin, count);
+            if (rc != MPE_OK) break;
+            for (int i = 0; i < p->A && e == cudaSuccess; ++i)
+                e = cudaMemcpyAsync(obs_n_host[i] + begin * p->obs_dim[i], obs_n_dev[i] + begin * p->obs_dim[i],
+                                    sizeof(float) * count * p->obs_dim[i], cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess)   // rew / done / info are [rows][n_env]: one strided copy per array
+                e = cudaMemcpy2DAsync(rew_host + begin, sizeof(float) * n, rew_dev + begin, sizeof(float) * n,
+                                      sizeof(float) * count, p->A, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess)
+                e = cudaMemcpy2DAsync(done_host + begin, n, done_dev + begin, n, count, p->A, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess && want_info)
+                e = cudaMemcpy2DAsync(info_host + begin, sizeof(float) * n, info_dev + begin, sizeof(float) * n,
+                                      sizeof(float) * count, static_cast<size_t>(p->A) * p->INFO, cudaMemcpyDeviceToHost, s);
+            if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync(D2H chunk)");
+        }
+        for (int k = 0; k < 2; ++k) {   // join, even after an error, so that the caller's stream stays ordered
+            cudaError_t j = cudaEventRecord(h->ev_join[k], h->aux[k]);
+            if (j == cudaSuccess) j = cudaStreamWaitEvent(user, h->ev_join[k], 0);
+            if (j != cudaSuccess && rc == MPE_OK) rc = cuda_fail(j, "mpe_step_host: join");
+        }
     }
     if (prev != h->device) cudaSetDevice(prev);
     return rc;

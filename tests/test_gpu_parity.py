@@ -241,9 +241,12 @@ def test_unaligned_action_views_are_handled():
         assert torch.equal(x, y)
 
 
-def test_host_buffers_path_equals_device_path():
-    """NumPy in -> NumPy out through mpe_step_host equals the CUDA-tensor path bit for bit"""
-    n = 2048
+@pytest.mark.parametrize("n", [2048, 70001])
+def test_host_buffers_path_equals_device_path(n):
+    """NumPy in -> NumPy out through mpe_step_host equals the CUDA-tensor path bit for bit (70001 worlds take
+    the chunk-pipelined route: 4 ranges over two internal streams, ragged last range)"""
+    import os
+    os.environ["MPE_B200_HOST_CHUNK_MIN"] = "16384"      # read once by the library, before its first host step
     env_a = make_product_env("simple_world_comm", num_envs=n)
     env_b = make_product_env("simple_world_comm", num_envs=n)
     env_a.reset()

@@ -36,7 +36,7 @@ def main():
     out = open(args.out, "w") if args.out else None
     for sc in args.scenarios.split(","):
         for n in [int(x) for x in args.sizes.split(",")]:
-            spec = SCENARIOS[sc]
+            spec = SCENARIOS.get(sc, dict(name=sc, kw={}))
             probe = make_env(spec["name"], num_envs=n, device=dev, **spec["kw"])
             bpe = probe.world.native_shapes().bytes_per_env_step
             ring_n = max(2, min(64, int(2.2 * 126 * 2**20 / (bpe * n)) + 1))
