@@ -451,12 +451,6 @@ static int cuda_fail(cudaError_t e, const char *what) {
         if (e_ != cudaSuccess) return cuda_fail(e_, #expr); \
     } while (0)
 
-static uint32_t mask_of(const uint8_t *v, int n) {
-    uint32_t m = 0;
-    for (int i = 0; i < n; ++i) if (v[i]) m |= 1u << i;
-    return m;
-}
-
 extern "C" int mpe_create(const mpe_desc *desc, int64_t n_env, int device, mpe_handle *out) {
     if (!desc || !out || n_env <= 0) return MPE_ERR_BAD_ARG;
     if (desc->abi_version != MPE_ABI_VERSION) return MPE_ERR_BAD_DESC;
@@ -520,11 +514,6 @@ extern "C" int mpe_create(const mpe_desc *desc, int64_t n_env, int device, mpe_h
         d.a_max_speed[i] = desc->agent_max_speed[i] < 0 ? -1.0f : static_cast<float>(desc->agent_max_speed[i]);
     }
     for (int l = 0; l < desc->n_landmarks; ++l) d.l_size[l] = static_cast<float>(desc->landmark_size[l]);
-    d.a_movable = mask_of(desc->agent_movable, desc->n_agents);
-    d.a_collide = mask_of(desc->agent_collide, desc->n_agents);
-    d.a_silent = mask_of(desc->agent_silent, desc->n_agents);
-    d.a_adversary = mask_of(desc->agent_adversary, desc->n_agents);
-    d.l_collide = mask_of(desc->landmark_collide, desc->n_landmarks);
     *out = h;
     return MPE_OK;
 }

@@ -31,7 +31,6 @@ __device__ __forceinline__ float pick(const float (&v)[N], int idx) {
     return r;
 }
 
-__host__ __device__ constexpr uint32_t low_bits(int n) { return n >= 32 ? 0xffffffffu : ((1u << n) - 1u); }
 
 // does the descriptor carry exactly the structural flags a program was compiled for?
 template <class P>

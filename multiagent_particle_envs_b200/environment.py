@@ -136,7 +136,7 @@ class MultiAgentEnv(_Env):
             nw.step(_lib.ptr_array([t.data_ptr() for t in payload]), out, flags, with_info=self._native_info)
             self._last_out = out
             world._obs_valid = False
-            return self._pack_batched(nw, out, payload)
+            return self._pack_batched(nw, out)
         # host callers: pinned staging -> mpe_step_host -> pinned outputs
         hs = nw.host_staging()
         ptrs = []
@@ -153,7 +153,7 @@ class MultiAgentEnv(_Env):
         if not world.batched:
             return self._pack_scalar(nw, hout)
         as_numpy = not hasattr(action_n[0], "dim")
-        return self._pack_batched(nw, hout, None, as_numpy=as_numpy)
+        return self._pack_batched(nw, hout, as_numpy=as_numpy)
 
     # ---- input classification ---------------------------------------------------------------
     def _to_cpu_tensor(self, a, i):
@@ -203,7 +203,7 @@ class MultiAgentEnv(_Env):
             return [nw.benchmark_data(i, batched, out) for i in range(self.n)]
         return [self.info_callback(agent, self.world) for agent in self.agents]
 
-    def _pack_batched(self, nw, out, _inputs, as_numpy=False):
+    def _pack_batched(self, nw, out, as_numpy=False):
         import torch
         obs_n = list(out.obs)
         reward_n = [out.rew[i] for i in range(self.n)]

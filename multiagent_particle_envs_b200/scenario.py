@@ -24,10 +24,6 @@ class BaseScenario(object):
 class NativeScenario(BaseScenario):
     """Shared implementation of the callback surface for scenarios that have a native program."""
 
-    #: half-width of the uniform reset distribution: agents, landmarks
-    agent_range = 1.0
-    landmark_range = 1.0
-
     def _finish_world(self, world, num_envs=None, device=None):
         world.native_program = self.native_program
         world.scenario = self

@@ -13,7 +13,6 @@ from ..scenario import NativeScenario
 
 class Scenario(NativeScenario):
     native_program = "simple_tag"
-    landmark_range = 0.9   # simple_tag.py:53
 
     def make_world(self, num_envs=None, device=None):
         world = World()

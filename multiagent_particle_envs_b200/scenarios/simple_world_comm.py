@@ -17,7 +17,6 @@ from ..scenario import NativeScenario
 
 class Scenario(NativeScenario):
     native_program = "simple_world_comm"
-    landmark_range = 0.9   # simple_world_comm.py:105-113
 
     def make_world(self, num_envs=None, device=None):
         world = World()
