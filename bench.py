@@ -143,7 +143,15 @@ def cpu_numpy_port(budget_s, steps=None, warmup=100, max_seconds=None):
     t0 = time.perf_counter()
     total, rates = np_port.timed_throughput(desc, procs, warmup, steps)
     dt = time.perf_counter() - t0
-    return {"value": total, "unit": UNIT, "cores": procs, "kind": "port",
+    cpu_model = ""
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                cpu_model = ln.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    return {"value": total, "unit": UNIT, "cores": procs, "kind": "port", "cpu_model": cpu_model,
             "sample": "%d processes (best of the probed counts; affinity reports %d CPUs) x %d env.step calls of one "
                       "simple_spread world each (oracle/np_port.py: per-world NumPy float64 restatement at the reference's "
                       "granularity, softmax actions, reset every 25 steps); %.1f s wall"
@@ -192,7 +200,7 @@ def cpu_c_oracle(budget_s, n_sample=N_ENV):
 
 def cpu_baseline_block(numpy_seconds, c_seconds):
     cb = cpu_numpy_port(numpy_seconds)
-    out = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    out = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "cpu_model")}
     out["per_process"] = cb["per_process"]
     if c_seconds > 0:
         c = cpu_c_oracle(c_seconds)
@@ -211,7 +219,7 @@ def run_reference_arm(args, rank, world):
     res = cpu_numpy_port(0, steps=args.steps, warmup=min(max(args.warmup, 3), 300), max_seconds=75.0)
     steps_timed = res["steps_per_process"]
     cores = res["cores"]
-    cb = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    cb = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "cpu_model")}
     cb["per_process"] = res["per_process"]
     c = cpu_c_oracle(5.0)
     cb["c_oracle"] = {k: c[k] for k in ("value", "unit", "cores", "sample")}

@@ -14,6 +14,7 @@
 #include <utility>
 
 #include "mpe_scenarios.cuh"
+#include "mpe_spread_lanes.cuh"
 
 namespace mpe {
 
@@ -88,19 +89,15 @@ __device__ __forceinline__ void physics(const DevDesc &d, typename P::W &w, cons
             const float bx = b_agent ? w.px[bi] : w.lx[bl];
             const float by = b_agent ? w.py[bi] : w.ly[bl];
             const float sb = b_agent ? d.a_size[bi] : d.l_size[bl];
-            const float dx = w.px[a] - bx, dy = w.py[a] - by;              // :186
-            const float dist = sqrt_rn_nobranch(fmaf(dx, dx, dy * dy));     // :187 (exact sqrt: dist - dist_min cancels)
-            const float dist_min = d.a_size[a] + sb;                        // :189
-            const float pen = softplus_fast((dist_min - dist) * d.inv_margin) * k;   // :191-192
-            const float s = __fdividef(cf * pen, dist);                     // :193  force = cf * delta / dist * pen
-            const float f_x = s * dx, f_y = s * dy;
+            const float2 f = pair_force(__fsub_rn(w.px[a], bx), __fsub_rn(w.py[a], by), __fadd_rn(d.a_size[a], sb),
+                                        cf, k, d.inv_margin);                // :186-193
             if (P::movable(a)) {                                            // :194, 149-151
-                fx[a] += f_x;
-                fy[a] += f_y;
+                fx[a] = __fadd_rn(fx[a], f.x);
+                fy[a] = __fadd_rn(fy[a], f.y);
             }
             if (b_agent && P::movable(bi)) {                                // :195, 152-154
-                fx[bi] -= f_x;
-                fy[bi] -= f_y;
+                fx[bi] = __fsub_rn(fx[bi], f.x);
+                fy[bi] = __fsub_rn(fy[bi], f.y);
             }
         }
     }
@@ -108,19 +105,9 @@ __device__ __forceinline__ void physics(const DevDesc &d, typename P::W &w, cons
 #pragma unroll
     for (int i = 0; i < A; ++i) {
         if (!P::movable(i)) continue;
-        float vx = fmaf(fx[i], d.a_dt_over_mass[i], w.vx[i] * d.keep);     // :161,163
-        float vy = fmaf(fy[i], d.a_dt_over_mass[i], w.vy[i] * d.keep);
-        if constexpr (P::kSpeedLimit) {                                     // :164-168
-            const float ms = d.a_max_speed[i];
-            const float speed = sqrt_rn_nobranch(fmaf(vx, vx, vy * vy));
-            const float sc = speed > ms ? __fdividef(ms, speed) : 1.0f;
-            vx *= sc;
-            vy *= sc;
-        }
-        w.px[i] = fmaf(vx, d.dt, w.px[i]);                                  // :169
-        w.py[i] = fmaf(vy, d.dt, w.py[i]);
-        w.vx[i] = vx;
-        w.vy[i] = vy;
+        const float4 r = integrate_entity<P::kSpeedLimit>(w.px[i], w.py[i], w.vx[i], w.vy[i], fx[i], fy[i], d.keep,
+                                                          d.a_dt_over_mass[i], d.dt, d.a_max_speed[i]);
+        w.px[i] = r.x; w.py[i] = r.y; w.vx[i] = r.z; w.vy[i] = r.w;
     }
 }
 
@@ -381,6 +368,8 @@ struct Program {
     bool (*validate)(const mpe_desc &);
     KernelFn fn[4];
     int smem_bytes;  // dynamic shared memory per WARP
+    KernelFn lanes_fn;  // lane-per-agent fused step (simple_spread only), else null
+    int lanes_smem, lanes_wpw;
     int A, L, NS, DIMC, INFO, G;
     int obs_dim[kMaxA], act_dim[kMaxA];
 };
@@ -400,11 +389,20 @@ static Program make_program() {
     return p;
 }
 
+template <int N>
+static Program make_spread_program() {
+    Program p = make_program<Spread<N>>();
+    p.lanes_fn = spread_lanes_kernel<N>;
+    p.lanes_smem = SpreadLanes<N>::kWarpBytes;
+    p.lanes_wpw = SpreadLanes<N>::WPW;
+    return p;
+}
+
 static const Program *programs(int *count) {
     static const Program table[] = {
         make_program<Simple<1, 1>>(),
-        make_program<Spread<2>>(), make_program<Spread<3>>(), make_program<Spread<4>>(),
-        make_program<Spread<5>>(), make_program<Spread<6>>(),
+        make_spread_program<2>(), make_spread_program<3>(), make_spread_program<4>(),
+        make_spread_program<5>(), make_spread_program<6>(),
         make_program<Tag<3, 1, 2>>(),
         make_program<WorldComm<4, 2, 1, 2>>(),
         make_program<Adversary<1, 2, 2>>(),
@@ -478,6 +476,8 @@ extern "C" int mpe_create(const mpe_desc *desc, int64_t n_env, int device, mpe_h
         CUDA_TRY(cudaSetDevice(device));
         for (int m = 0; m < 4; ++m)
             CUDA_TRY(cudaFuncSetAttribute(prog->fn[m], cudaFuncAttributeMaxDynamicSharedMemorySize, prog->smem_bytes * kMaxWarpsPerBlock));
+        if (prog->lanes_fn)
+            CUDA_TRY(cudaFuncSetAttribute(prog->lanes_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, prog->lanes_smem * kMaxWarpsPerBlock));
         CUDA_TRY(cudaSetDevice(prev));
     }
 
@@ -547,6 +547,8 @@ extern "C" int64_t mpe_bytes_per_env_step(mpe_handle h) {
     return 4 * f + p->A;
 }
 
+constexpr int64_t kLanesMaxWorlds = 0;  // set from measurements (see profiles/)
+
 static int pdl_mode() {  // 0 = off (default), 1 = late trigger, 2 = early trigger
     static const int m = [] { const char *e = getenv("MPE_B200_PDL"); return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0; }();
     return m;
@@ -558,6 +560,26 @@ static int launch(mpe_handle h, int mode, StepArgs &args, void *stream, int64_t 
     args.n = h->n;
     args.begin = begin;
     args.count = count < 0 ? h->n - begin : count;
+    // simple_spread fused steps may run on the lane-per-agent kernel (mpe_spread_lanes.cuh): MPE_B200_SPREAD_LANES
+    // = 0 never, 1 always, unset: up to kLanesMaxWorlds worlds, where the lane-per-world kernel has too few warps
+    static const int lanes_env = [] { const char *e = getenv("MPE_B200_SPREAD_LANES"); return e ? atoi(e) : -1; }();
+    const bool lanes = mode == kFusedStep && h->prog->lanes_fn != nullptr &&
+                       (lanes_env == 1 || (lanes_env < 0 && args.count <= kLanesMaxWorlds));
+    if (lanes) {
+        const int64_t lw = (args.count + h->prog->lanes_wpw - 1) / h->prog->lanes_wpw;
+        const int64_t lb = (lw + kMaxWarpsPerBlock - 1) / kMaxWarpsPerBlock;
+        int prev = 0;
+        CUDA_TRY(cudaGetDevice(&prev));
+        if (prev != h->device) CUDA_TRY(cudaSetDevice(h->device));
+        void *params[] = {&args};
+        cudaError_t e = cudaLaunchKernel(reinterpret_cast<const void *>(h->prog->lanes_fn), dim3(static_cast<unsigned>(lb)),
+                                         dim3(kMaxThreads), params, static_cast<size_t>(h->prog->lanes_smem) * kMaxWarpsPerBlock,
+                                         static_cast<cudaStream_t>(stream));
+        if (prev != h->device) cudaSetDevice(prev);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernel(spread_lanes)");
+        __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED);
+        return MPE_OK;
+    }
     const int64_t warps = (args.count + 31) / 32;
     // Warps are autonomous, so the block size only sets scheduling granularity (measured at 65536 worlds:
     // 1 / 2 / 4 warps per block = 6.69 / 6.34 / 7.06 us per step): tiny batches use one warp per block so

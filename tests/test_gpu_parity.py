@@ -265,3 +265,42 @@ def test_host_buffers_path_equals_device_path(n):
         for x, y in zip(ra, rb):
             assert np.array_equal(x.cpu().numpy(), y)
         assert not any(d.any() for d in db)
+
+
+_LANES_SCRIPT = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(root)r + "/tests")
+from helpers import make_product_env
+out = {}
+for tag, n in (("simple_spread_n3", 5003), ("simple_spread_n6", 2049)):
+    env = make_product_env(tag, num_envs=n, seed=21)
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(4)
+    for t in range(3):
+        acts = [torch.softmax(3 * torch.randn(n, 5, device="cuda", generator=g), 1) for _ in range(env.n)]
+        obs_n, rew_n, _, _ = env.step(acts)
+    out[tag + "_obs"] = torch.cat(obs_n, 1).cpu().numpy()
+    out[tag + "_rew"] = torch.stack(rew_n).cpu().numpy()
+    out[tag + "_pv"] = env.world.native.agent_pv.cpu().numpy()
+    out[tag + "_info"] = env._last_out.info.cpu().numpy()
+np.savez(sys.argv[1], **out)
+"""
+
+
+def test_lane_per_agent_spread_kernel_is_bit_identical(tmp_path):
+    """MPE_B200_SPREAD_LANES=1 routes simple_spread's fused step through the lane-per-agent kernel
+    (warp-shuffle exchange and min-reduction, csrc/mpe_spread_lanes.cuh); it must reproduce the default
+    lane-per-world kernel bit for bit, including partial warps (5003 and 2049 worlds)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for mode in ("0", "1"):
+        path = str(tmp_path / ("lanes%s.npz" % mode))
+        env = dict(os.environ, MPE_B200_SPREAD_LANES=mode)
+        subprocess.run([sys.executable, "-c", _LANES_SCRIPT % {"root": root}, path], check=True, env=env, timeout=600)
+        res[mode] = dict(np.load(path))
+    assert set(res["0"]) == set(res["1"]) and len(res["0"]) == 8
+    for k in res["0"]:
+        assert np.array_equal(res["0"][k], res["1"][k]), k
