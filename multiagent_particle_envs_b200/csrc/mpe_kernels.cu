@@ -138,7 +138,18 @@ __global__ void __launch_bounds__(kMaxThreads) mpe_kernel(const __grid_constant_
 #pragma unroll
         for (int i = 0; i < A; ++i) bits |= reinterpret_cast<uintptr_t>(a.act[i]);
         bulk = (rows == 32) && ((bits & 15u) == 0);   // warp-uniform
-        if (bulk && lane == 0) {
+        if (bulk && (a.flags & kFlagCpAsync)) {
+            // every lane copies 16-byte pieces of the (contiguous) tiles straight into shared memory
+            static_for<A>([&](auto ic) {
+                constexpr int i = decltype(ic)::value;
+                constexpr int AD = P::act_dim(i), kVec = 32 * AD / 4;
+                const float *g = a.act[i] + w0 * AD;
+                float *sdst = s_warp + Shape<P>::act_off(i);
+#pragma unroll
+                for (int q0 = 0; q0 < kVec; q0 += 32)
+                    if (q0 + 32 <= kVec || q0 + lane < kVec) cp_async16(sdst + 4 * (q0 + lane), g + 4 * (q0 + lane));
+            });
+        } else if (bulk && lane == 0) {
             // one UBLKCP per agent tile (32 rows x act_dim floats, contiguous in global memory)
             mbar_init(bar, 1);
             mbar_expect_tx(bar, Shape<P>::act_bytes_total());
@@ -177,7 +188,10 @@ __global__ void __launch_bounds__(kMaxThreads) mpe_kernel(const __grid_constant_
     float cact[NC > 0 ? NC : 1];
     // ---- MultiAgentEnv._set_action (environment.py:144-192) --------------------------------
     if constexpr (MODE == kFusedStep || MODE == kSetAction) {
-        if (bulk) {
+        if (bulk && (a.flags & kFlagCpAsync)) {
+            cp_async_wait_all();
+            __syncwarp();
+        } else if (bulk) {
             __syncwarp();
             mbar_wait(bar, 0);
         } else {
@@ -602,6 +616,10 @@ static int launch(mpe_handle h, int mode, StepArgs &args, void *stream, int64_t 
     cfg.attrs = attr;
     cfg.numAttrs = pdl_mode() ? 1 : 0;
     if (pdl_mode() == 2) args.flags |= kFlagPdlEarly;
+    // action tiles: cp.async (LDGSTS) by default -- measured 1-5 % faster than the TMA bulk copy + mbarrier at every
+    // batch size (no barrier init / proxy fence in the prologue); MPE_B200_ACT_STAGING=tma selects the TMA path
+    static const bool cpasync = [] { const char *e = getenv("MPE_B200_ACT_STAGING"); return !(e && e[0] == 't'); }();
+    if (cpasync) args.flags |= kFlagCpAsync;
     void *params[] = {&args};
     cudaError_t e = cudaLaunchKernelExC(&cfg, reinterpret_cast<const void *>(h->prog->fn[mode]), params);
     if (prev != h->device) cudaSetDevice(prev);
