@@ -136,6 +136,8 @@ class MultiAgentEnv(_Env):
             nw.step(_lib.ptr_array([t.data_ptr() for t in payload]), out, flags, with_info=self._native_info)
             self._last_out = out
             world._obs_valid = False
+            if not world.batched:     # scalar convention with device-side inputs (e.g. discrete_action_input)
+                return self._pack_scalar(nw, out)
             return self._pack_batched(nw, out)
         # host callers: pinned staging -> mpe_step_host -> pinned outputs
         hs = nw.host_staging()
@@ -219,10 +221,11 @@ class MultiAgentEnv(_Env):
         return obs_n, reward_n, done_n, info_n
 
     def _pack_scalar(self, nw, hout):
-        obs_n = [o[0].numpy().astype(np.float64) for o in hout.obs]
-        rew = hout.rew[:, 0].numpy().astype(np.float64)
+        obs_n = [o[0].detach().to("cpu").numpy().astype(np.float64) for o in hout.obs]
+        rew = hout.rew[:, 0].detach().to("cpu").numpy().astype(np.float64)
         reward_n = [rew[i] for i in range(self.n)]
-        done_n = [bool(hout.done[i, 0]) for i in range(self.n)]
+        done_host = hout.done[:, 0].detach().to("cpu")
+        done_n = [bool(done_host[i]) for i in range(self.n)]
         if self.done_callback is not None:
             done_n = [self.done_callback(agent, self.world) for agent in self.agents]
         info_n = {'n': self._info_list(nw, hout, False)}

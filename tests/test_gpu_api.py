@@ -92,6 +92,20 @@ def test_discrete_action_input(tag):
     np.testing.assert_allclose(nw.agent_pv.permute(1, 0, 2).cpu().numpy(), rpv, rtol=RTOL, atol=ATOL)
 
 
+def test_scalar_mode_with_integer_actions():
+    """reference usage: env.discrete_action_input = True; env.step([2, 4, 0]) on a single world"""
+    env = make_product_env("simple_spread_n3")
+    env.discrete_action_input = True
+    env.reset()
+    for ag in env.world.agents:
+        ag.state.p_vel = np.zeros(2)
+    obs_n, rew_n, done_n, info_n = env.step([1, 2, 4])
+    assert all(isinstance(o, np.ndarray) and o.dtype == np.float64 and o.shape == (18,) for o in obs_n)
+    assert all(isinstance(d, bool) for d in done_n) and isinstance(float(rew_n[0]), float)
+    # index 1 -> u.x = -1, 2 -> +1, 4 -> u.y = +1 (environment.py:163-167), sensitivity 5, dt 0.1
+    np.testing.assert_allclose([obs_n[0][0], obs_n[1][0], obs_n[2][1]], [-0.5, 0.5, 0.5], rtol=0, atol=0.05)
+
+
 @pytest.mark.parametrize("tag", list(CONFIGS))
 def test_scalar_convention_replays_reference_world(tag):
     """make_env(name) with no batch: lists of float64 ndarrays / floats / bools, world 0 of the golden
