@@ -97,13 +97,14 @@ def test_scalar_mode_with_integer_actions():
     env = make_product_env("simple_spread_n3")
     env.discrete_action_input = True
     env.reset()
-    for ag in env.world.agents:
+    for ag, p in zip(env.world.agents, ([-0.8, 0.0], [0.0, 0.8], [0.8, 0.0])):   # far apart: no contact forces
+        ag.state.p_pos = np.array(p)
         ag.state.p_vel = np.zeros(2)
     obs_n, rew_n, done_n, info_n = env.step([1, 2, 4])
     assert all(isinstance(o, np.ndarray) and o.dtype == np.float64 and o.shape == (18,) for o in obs_n)
     assert all(isinstance(d, bool) for d in done_n) and isinstance(float(rew_n[0]), float)
     # index 1 -> u.x = -1, 2 -> +1, 4 -> u.y = +1 (environment.py:163-167), sensitivity 5, dt 0.1
-    np.testing.assert_allclose([obs_n[0][0], obs_n[1][0], obs_n[2][1]], [-0.5, 0.5, 0.5], rtol=0, atol=0.05)
+    np.testing.assert_allclose([obs_n[0][0], obs_n[1][0], obs_n[2][1]], [-0.5, 0.5, 0.5], rtol=1e-6, atol=1e-6)
 
 
 @pytest.mark.parametrize("tag", list(CONFIGS))
