@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmpe_b200.so")
+LIB_PATH = os.environ.get("MPE_B200_LIB") or os.path.join(_HERE, "csrc", "libmpe_b200.so")   # override: kernel A/B experiments
 
 MPE_ABI_VERSION = 1
 MPE_MAX_AGENTS = 8

@@ -166,12 +166,12 @@ __global__ void __launch_bounds__(kMaxThreads) mpe_kernel(const __grid_constant_
     if constexpr (MODE != kSetAction) {
 #pragma unroll
         for (int i = 0; i < A; ++i) {
-            const float4 v = a.pv[i * n + wi];
+            const float4 v = state_load(a.pv + i * n + wi);
             w.px[i] = v.x; w.py[i] = v.y; w.vx[i] = v.z; w.vy[i] = v.w;
         }
 #pragma unroll
         for (int l = 0; l < L; ++l) {
-            const float2 v = a.lm[l * n + wi];
+            const float2 v = state_load(a.lm + l * n + wi);
             w.lx[l] = v.x; w.ly[l] = v.y;
         }
         if constexpr (MODE == kObserve && NC > 0) {
