@@ -206,11 +206,9 @@ class MultiAgentEnv(_Env):
         return [self.info_callback(agent, self.world) for agent in self.agents]
 
     def _pack_batched(self, nw, out, as_numpy=False):
-        import torch
         obs_n = list(out.obs)
-        reward_n = [out.rew[i] for i in range(self.n)]
-        done_b = out.done.view(torch.bool)
-        done_n = [done_b[i] for i in range(self.n)]
+        reward_n = list(out.rew_list)
+        done_n = list(out.done_list)
         if self.done_callback is not None:
             done_n = [self.done_callback(agent, self.world) for agent in self.agents]
         info_n = {'n': self._info_list(nw, out, True)}

@@ -88,6 +88,10 @@ class Outputs(object):
         if nw.info_dim > 0:
             self.info = s[info_off:info_off + A * nw.info_dim * N * 4].view(torch.float32).view(A, nw.info_dim, N)
         self.done = s[done_off:done_off + A * N].view(A, N)
+        # per-agent views handed to the caller (built once: persistent outputs are reused every step)
+        self.rew_list = [self.rew[i] for i in range(A)]
+        done_b = self.done.view(torch.bool)
+        self.done_list = [done_b[i] for i in range(A)]
         self.obs_ptrs = _lib.ptr_array([t.data_ptr() for t in self.obs])
         self.rew_ptr = self.rew.data_ptr()
         self.done_ptr = self.done.data_ptr()
