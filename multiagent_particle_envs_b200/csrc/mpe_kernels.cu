@@ -112,7 +112,7 @@ __device__ __forceinline__ void physics(const DevDesc &d, typename P::W &w, cons
 }
 
 #ifndef MPE_MIN_BLOCKS
-#define MPE_MIN_BLOCKS 4   // measured: 1-3 % faster than 1 on world_comm / spread N=6 (128-register budget), neutral elsewhere
+#define MPE_MIN_BLOCKS 1   // 512-thread bound x 1 block = the same 128-register budget that measured best
 #endif
 
 template <class P, int MODE>
@@ -440,6 +440,12 @@ static const Program *programs(int *count) {
 // =================================================================================================
 using namespace mpe;
 
+// largest block (in warps) whose warp-private staging fits the 227 KB of dynamic shared memory of an SM
+static int max_warps_per_block(int smem_per_warp) {
+    const int fit = (227 * 1024) / (smem_per_warp > 0 ? smem_per_warp : 1);
+    return fit < 1 ? 1 : (fit > kMaxWarpsPerBlock ? kMaxWarpsPerBlock : fit);
+}
+
 static_assert(sizeof(mpe_desc) == 480, "mpe_desc layout is part of the ABI (mirrored by _lib.MpeDesc)");
 
 struct mpe_env {
@@ -493,9 +499,10 @@ extern "C" int mpe_create(const mpe_desc *desc, int64_t n_env, int device, mpe_h
         CUDA_TRY(cudaGetDevice(&prev));
         CUDA_TRY(cudaSetDevice(device));
         for (int m = 0; m < 4; ++m)
-            CUDA_TRY(cudaFuncSetAttribute(prog->fn[m], cudaFuncAttributeMaxDynamicSharedMemorySize, prog->smem_bytes * kMaxWarpsPerBlock));
+            CUDA_TRY(cudaFuncSetAttribute(prog->fn[m], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          prog->smem_bytes * max_warps_per_block(prog->smem_bytes)));
         if (prog->lanes_fn)
-            CUDA_TRY(cudaFuncSetAttribute(prog->lanes_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, prog->lanes_smem * kMaxWarpsPerBlock));
+            CUDA_TRY(cudaFuncSetAttribute(prog->lanes_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, prog->lanes_smem * 4));
         CUDA_TRY(cudaSetDevice(prev));
     }
 
@@ -585,13 +592,14 @@ static int launch(mpe_handle h, int mode, StepArgs &args, void *stream, int64_t 
                        (lanes_env == 1 || (lanes_env < 0 && args.count <= kLanesMaxWorlds));
     if (lanes) {
         const int64_t lw = (args.count + h->prog->lanes_wpw - 1) / h->prog->lanes_wpw;
-        const int64_t lb = (lw + kMaxWarpsPerBlock - 1) / kMaxWarpsPerBlock;
+        constexpr int kLanesWpb = 4;
+        const int64_t lb = (lw + kLanesWpb - 1) / kLanesWpb;
         int prev = 0;
         CUDA_TRY(cudaGetDevice(&prev));
         if (prev != h->device) CUDA_TRY(cudaSetDevice(h->device));
         void *params[] = {&args};
         cudaError_t e = cudaLaunchKernel(reinterpret_cast<const void *>(h->prog->lanes_fn), dim3(static_cast<unsigned>(lb)),
-                                         dim3(kMaxThreads), params, static_cast<size_t>(h->prog->lanes_smem) * kMaxWarpsPerBlock,
+                                         dim3(32 * kLanesWpb), params, static_cast<size_t>(h->prog->lanes_smem) * kLanesWpb,
                                          static_cast<cudaStream_t>(stream));
         if (prev != h->device) cudaSetDevice(prev);
         if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernel(spread_lanes)");
@@ -602,8 +610,9 @@ static int launch(mpe_handle h, int mode, StepArgs &args, void *stream, int64_t 
     // Warps are autonomous, so the block size only sets scheduling granularity (measured at 65536 worlds:
     // 1 / 2 / 4 warps per block = 6.69 / 6.34 / 7.06 us per step): tiny batches use one warp per block so
     // that the few blocks spread over all 148 SMs, mid-size batches two, large ones four.
-    static const int wpb_env = [] { const char *e = getenv("MPE_B200_WPB"); int v = e ? atoi(e) : 0; return (v == 1 || v == 2 || v == 4) ? v : 0; }();
-    const int wpb = wpb_env ? wpb_env : (warps <= 148 * 4 ? 1 : (warps <= 148 * 64 ? 2 : kMaxWarpsPerBlock));
+    static const int wpb_env = [] { const char *e = getenv("MPE_B200_WPB"); int v = e ? atoi(e) : 0; return (v >= 1 && v <= kMaxWarpsPerBlock) ? v : 0; }();
+    int wpb = wpb_env ? wpb_env : (warps <= 148 * 4 ? 1 : (warps <= 148 * 64 ? 2 : 4));
+    if (wpb > max_warps_per_block(h->prog->smem_bytes)) wpb = max_warps_per_block(h->prog->smem_bytes);
     const int64_t blocks = (warps + wpb - 1) / wpb;
     if (blocks > 0x7fffffffLL) return MPE_ERR_BAD_ARG;
     int prev = 0;

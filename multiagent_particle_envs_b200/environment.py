@@ -83,7 +83,7 @@ class MultiAgentEnv(_Env):
         self._act_dims = list(shapes.act_dims)
         self._sub_sizes = [([5] if a.movable else []) + ([world.dim_c] if not a.silent else []) for a in self.agents]
 
-        # rendering (no GUI on this path; attributes kept for API compatibility)
+        # rendering (headless; attributes kept for API compatibility)
         self.shared_viewer = shared_viewer
         self.viewers = [None] if shared_viewer else [None] * self.n
         self._reset_render()
@@ -289,11 +289,39 @@ class MultiAgentEnv(_Env):
         if new_c is not None:
             nw.act_c[s * nw.dim_c:(s + 1) * nw.dim_c] = new_c
 
-    # ---- rendering: out of scope on this path ---------------
+    # ---- rendering: a headless rasteriser stands in for the pyglet viewer ---
     def _reset_render(self):
         self.render_geoms = None
         self.render_geoms_xform = None
 
-    def render(self, mode='human'):
-        raise NotImplementedError("rendering (pyglet) is outside the B200 hot path; use the reference's viewer "
-                                  "on states read back through entity.state.p_pos")
+    def render(self, mode='human', world_index=0):
+        """environment.py:200-263 without a window: returns one uint8 [700, 700, 3] image per viewer
+        (one shared viewer, or one per agent when shared_viewer=False) of world `world_index`;
+        mode 'human' additionally prints the communication line the reference prints (:201-213)."""
+        from .raster import draw_world
+        world = self.world
+        nw = world.bind()
+        pv = nw.agent_pv[:, world_index].detach().to("cpu").numpy().astype(np.float64)
+        lm = nw.lm_p[:, world_index].detach().to("cpu").numpy().astype(np.float64)[:len(world.landmarks)]
+        if mode == 'human':
+            alphabet = 'ABCDEFGHIJKLMNOPQRSTUVWXYZ'
+            message = ''
+            for agent in world.agents:
+                for i, other in enumerate(world.agents):
+                    if other is agent:
+                        continue
+                    s = nw.speaker_slot(i)
+                    c = np.zeros(0) if s < 0 else nw.comm[s * nw.dim_c:(s + 1) * nw.dim_c, world_index].detach().to("cpu").numpy()
+                    word = '_' if (c.size == 0 or np.all(c == 0)) else alphabet[int(np.argmax(c))]
+                    message += (other.name + ' to ' + agent.name + ': ' + word + '   ')
+            print(message)
+        ents = world.entities
+        pos = np.concatenate([pv[:, 0:2], lm], axis=0) if len(lm) else pv[:, 0:2]
+        sizes = [e.size for e in ents]
+        colors = [e.color for e in ents]
+        alphas = [0.5 if 'agent' in e.name else 1.0 for e in ents]
+        results = []
+        for i in range(len(self.viewers)):
+            center = (0.0, 0.0) if self.shared_viewer else tuple(pv[i, 0:2])
+            results.append(draw_world(pos, sizes, colors, alphas, center=center))
+        return results

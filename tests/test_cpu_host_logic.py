@@ -203,3 +203,14 @@ def test_two_rank_gloo_sharding_and_counter():
     for rank, total, tmax, per_rank in res:
         assert total == 10010.0 and tmax == 1.5
         assert per_rank == [(5010.0, 0.5), (5000.0, 1.5)]
+
+
+def test_headless_rasteriser_draws_circles():
+    from multiagent_particle_envs_b200.raster import draw_world
+    img = draw_world(np.array([[0.0, 0.0], [0.5, 0.5]]), [0.2, 0.1], [np.array([1.0, 0, 0]), np.array([0, 0, 1.0])], [1.0, 0.5])
+    assert img.shape == (700, 700, 3) and img.dtype == np.uint8
+    assert tuple(img[350, 350]) == (255, 0, 0)                    # opaque red disc at the origin
+    assert tuple(img[175, 525]) == (128, 128, 255)                # half-transparent blue at (0.5, 0.5): y axis points up
+    assert tuple(img[10, 10]) == (255, 255, 255)
+    area = (img[:, :, 1] == 0).sum() / 700.0 ** 2 * 4.0           # red disc area in world units
+    assert abs(area - np.pi * 0.2 ** 2) < 0.003

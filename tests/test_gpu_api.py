@@ -60,8 +60,9 @@ def test_scenario_callbacks_and_env_accessors():
     env._set_action(a, world.agents[2], env.action_space[2])
     u = world.agents[2].action.u
     assert torch.allclose(u, torch.tensor([5.0, 0.0], device="cuda").expand(n, 2))
-    with pytest.raises(NotImplementedError):
-        env.render()
+    frames = env.render('rgb_array')                                  # headless stand-in for the pyglet viewer
+    assert len(frames) == 1 and frames[0].shape == (700, 700, 3) and frames[0].dtype == np.uint8
+    assert (frames[0] != 255).any() and (frames[0] == 255).mean() > 0.5
 
 
 @pytest.mark.parametrize("tag", ["simple_tag", "simple_world_comm", "simple_speaker_listener"])
