@@ -45,12 +45,19 @@ METRIC = "env_steps_per_sec"
 UNIT = "env-steps/s"
 
 
+SCENARIO_KW = {}
+BYTES_PER_ENV_STEP = 411
+N_AGENTS = 3
+
+
 def workload_config(n_gpus, ring):
-    return {"workload": "simple_spread N=3 agents/landmarks, batch=65536 worlds per GPU (BASELINE configs[1])",
+    headline = (SCENARIO == "simple_spread" and N_ENV == 65536 and not SCENARIO_KW)
+    return {"workload": ("simple_spread N=3 agents/landmarks, batch=65536 worlds per GPU (BASELINE configs[1])" if headline
+                         else "%s %s, batch=%d worlds per GPU" % (SCENARIO, SCENARIO_KW or "", N_ENV)),
             "scenario": SCENARIO, "n_env_per_gpu": N_ENV, "global_n_env": N_ENV * n_gpus,
-            "agents": 3, "episode_length": EPISODE, "ring_batches": ring,
+            "agents": N_AGENTS, "episode_length": EPISODE, "ring_batches": ring,
             "l2_policy": ("inputs larger than L2: steps rotate over %d independent batches (%.0f MB > 2x126 MB)"
-                          % (ring, ring * N_ENV * 411 / 1e6)) if ring > 1 else "n/a (CPU arm)",
+                          % (ring, ring * N_ENV * BYTES_PER_ENV_STEP / 1e6)) if ring > 1 else "n/a (CPU arm)",
             "actions": "softmax of N(0,1) logits, pre-generated per batch, resident in HBM",
             "parallelism": "dp%d (independent shards, no data-path collective)" % n_gpus}
 
@@ -113,7 +120,7 @@ class ClockSampler(object):
 # ------------------------------------------------------------------------------------------------
 def _spread_desc():
     from multiagent_particle_envs_b200 import make_env
-    return make_env(SCENARIO).world.descriptor()
+    return make_env(SCENARIO, **SCENARIO_KW).world.descriptor()
 
 
 def _best_process_count(desc):
@@ -221,8 +228,9 @@ def run_reference_arm(args, rank, world):
     cores = res["cores"]
     cb = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "cpu_model")}
     cb["per_process"] = res["per_process"]
-    c = cpu_c_oracle(5.0)
-    cb["c_oracle"] = {k: c[k] for k in ("value", "unit", "cores", "sample")}
+    if SCENARIO == "simple_spread" and not SCENARIO_KW:
+        c = cpu_c_oracle(5.0)
+        cb["c_oracle"] = {k: c[k] for k in ("value", "unit", "cores", "sample")}
     line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "steps_timed_per_process": steps_timed, "warmup": args.warmup,
             "ms_per_step": 1e3 * cores / res["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -256,14 +264,23 @@ def run_b200_arm(args, rank, local_rank, world):
     ring = []
     R = args.ring
     for b in range(R):
-        env = make_env(SCENARIO, num_envs=N_ENV * world, device=dev, seed=1000 + b, rank=rank, world_size=world)
+        env = make_env(SCENARIO, num_envs=N_ENV * world, device=dev, seed=1000 + b, rank=rank, world_size=world,
+                       **SCENARIO_KW)
         env.reset()
         nw = env.world.native
         bytes_per_step = nw.bytes_per_env_step * N_ENV
         g = torch.Generator(device=dev).manual_seed(7 * b + rank)
-        acts = [torch.softmax(torch.randn(N_ENV, 5, device=dev, generator=g), 1).contiguous() for _ in range(env.n)]
+        acts = []
+        for d_act, ag in zip(nw.act_dims, env.agents):     # 5 movement probabilities, then the utterance
+            parts = []
+            if ag.movable:
+                parts.append(torch.softmax(torch.randn(N_ENV, 5, device=dev, generator=g), 1))
+            if d_act - (5 if ag.movable else 0) > 0:
+                parts.append(torch.rand(N_ENV, d_act - (5 if ag.movable else 0), device=dev, generator=g))
+            acts.append(torch.cat(parts, 1).contiguous())
         ring.append((env, nw, acts, _lib.ptr_array([t.data_ptr() for t in acts]), env._flags()))
-    assert R * bytes_per_step > 2 * L2_BYTES, "ring working set must exceed 2x L2"
+    if R * bytes_per_step <= 2 * L2_BYTES:
+        raise SystemExit("ring working set (%d x %.0f MB) must exceed 2x L2: raise --ring" % (R, bytes_per_step / 1e6))
     stream = torch.cuda.Stream(dev)
     launches = [0]
 
@@ -354,24 +371,27 @@ def run_b200_arm(args, rank, local_rank, world):
         achieved = bytes_per_step / launch_s / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
+        if os.path.exists(tp) and SCENARIO == "simple_spread" and N_ENV == 65536 and not SCENARIO_KW:
             try:
                 traffic = json.load(open(tp)).get("simple_spread_65536_dram_bytes_per_launch")
             except Exception:  # noqa: BLE001
                 traffic = None
-        cpu = cpu_baseline_block(args.cpu_seconds, 5.0)[0] if world == 1 and args.cpu_seconds > 0 else None
+        cpu = None
+        if world == 1 and args.cpu_seconds > 0 and SCENARIO in ("simple", "simple_spread", "simple_tag", "simple_world_comm"):
+            cpu = cpu_baseline_block(args.cpu_seconds, 5.0 if SCENARIO == "simple_spread" and not SCENARIO_KW else 0.0)[0]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": 1e3 * launch_s, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(world, R),
-            "agent_steps_per_sec": 3 * value,
+            "agent_steps_per_sec": N_AGENTS * value,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": k_e2e, "ms_per_step": 1e3 * e2e_max / k_e2e, "api": "MultiAgentEnv.step(pinned host tensors)"},
             "gpu_launches": gpu_launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": bytes_per_step, "kernel": "mpe_kernel<Spread<3>, kFusedStep>"},
+                         "algorithmic_bytes_per_launch": bytes_per_step,
+                         "kernel": "mpe_kernel<%s program, kFusedStep>" % SCENARIO},
             "per_rank": per_rank,
         }
         if cpu is not None:
@@ -390,7 +410,19 @@ def main():
     ap.add_argument("--ring", type=int, default=12)
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--scenario", default="simple_spread", help="other BASELINE configs: simple_tag, simple_world_comm, ...")
+    ap.add_argument("--num-envs", type=int, default=65536, help="worlds per GPU")
+    ap.add_argument("--num-agents", type=int, default=None, help="simple_spread only (N agents = N landmarks)")
     args = ap.parse_args()
+    global SCENARIO, N_ENV, SCENARIO_KW, BYTES_PER_ENV_STEP, N_AGENTS
+    SCENARIO, N_ENV = args.scenario, args.num_envs
+    if args.num_agents is not None:
+        SCENARIO_KW = {"num_agents": args.num_agents}
+    from multiagent_particle_envs_b200 import make_env as _mk
+    _probe = _mk(SCENARIO, **SCENARIO_KW)
+    BYTES_PER_ENV_STEP, N_AGENTS = _probe.world.native_shapes().bytes_per_env_step, _probe.n
+    if args.ring * N_ENV * BYTES_PER_ENV_STEP <= 2 * L2_BYTES:
+        args.ring = int(2 * L2_BYTES / (N_ENV * BYTES_PER_ENV_STEP)) + 2
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

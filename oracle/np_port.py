@@ -234,9 +234,9 @@ def _worker(args):
     def acts():
         out = []
         for dmn in adims:
-            z = rng.randn(dmn)
+            z = rng.randn(5)
             e = np.exp(z - z.max())
-            out.append(e / e.sum())
+            out.append(np.concatenate([e / e.sum(), rng.uniform(0, 1, dmn - 5)]))
         return out
 
     for t in range(warmup):
