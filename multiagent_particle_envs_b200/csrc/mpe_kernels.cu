@@ -421,9 +421,10 @@ static const Program *programs(int *count) {
         make_program<Simple<1, 1>>(),
         make_spread_program<2>(), make_spread_program<3>(), make_spread_program<4>(),
         make_spread_program<5>(), make_spread_program<6>(),
-        make_program<Tag<3, 1, 2>>(),
+        make_program<Tag<3, 1, 2>>(), make_program<Tag<1, 1, 2>>(), make_program<Tag<2, 1, 2>>(),
+        make_program<Tag<4, 2, 2>>(), make_program<Tag<6, 2, 3>>(),
         make_program<WorldComm<4, 2, 1, 2>>(),
-        make_program<Adversary<1, 2, 2>>(),
+        make_program<Adversary<1, 2, 2>>(), make_program<Adversary<1, 3, 3>>(),
         make_program<Push<1, 1, 2>>(),
         make_program<SpeakerListener>(),
         make_program<Reference>(),

@@ -5,7 +5,8 @@ good agents' reward (:76-105): -min_good |good - goal| + sum_adv |adv - goal|; a
 -|adv - goal|^2.  Observation (:121-139): good = [goal - pos, landmarks - pos, others - pos] (10 floats),
 adversary = [landmarks - pos, others - pos] (8 floats; it does not see which landmark is the goal).
 The goal index is drawn per world at reset (np.random.choice(world.landmarks), :44) and lives in
-`world.native.goal[0]`.  Native program: Adversary<1,2,2> in csrc/mpe_scenarios.cuh."""
+`world.native.goal[0]`.  Native program: Adversary<1,NGOOD,NGOOD> in csrc/mpe_scenarios.cuh, compiled for NGOOD = 2
+(the reference) and 3 via Scenario(num_agents=4)."""
 import numpy as np
 
 from ..core import World, Agent, Landmark
@@ -15,10 +16,13 @@ from ..scenario import NativeScenario
 class Scenario(NativeScenario):
     native_program = "simple_adversary"
 
+    def __init__(self, num_agents=3):
+        self.num_agents = num_agents
+
     def make_world(self, num_envs=None, device=None):
         world = World()
         world.dim_c = 2
-        num_agents, num_adversaries = 3, 1
+        num_agents, num_adversaries = self.num_agents, 1
         world.num_agents = num_agents
         world.agents = [Agent() for _ in range(num_agents)]
         for i, agent in enumerate(world.agents):

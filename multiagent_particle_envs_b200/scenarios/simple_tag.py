@@ -4,7 +4,8 @@ obstacles (reference: multiagent/scenarios/simple_tag.py).
 prey reward: -10 per adversary in contact, minus bound(|x|) + bound(|y|) for leaving the arena
 (:89-113); every adversary: +10 per (prey, adversary) pair in contact (:115-129).
 Observation: [vel, pos, obstacles - pos, others - pos, prey velocities] (:131-147).
-Native program: Tag<3,1,2> in csrc/mpe_scenarios.cuh."""
+Native program: Tag<NADV,NGOOD,L> in csrc/mpe_scenarios.cuh; compiled for (3,1,2) -- the reference's counts --
+and (1,1,2), (2,1,2), (4,2,2), (6,2,3) via Scenario(num_adversaries=, num_good_agents=, num_landmarks=)."""
 import numpy as np
 
 from ..core import World, Agent, Landmark
@@ -14,10 +15,13 @@ from ..scenario import NativeScenario
 class Scenario(NativeScenario):
     native_program = "simple_tag"
 
+    def __init__(self, num_adversaries=3, num_good_agents=1, num_landmarks=2):
+        self.counts = (num_good_agents, num_adversaries, num_landmarks)
+
     def make_world(self, num_envs=None, device=None):
         world = World()
         world.dim_c = 2
-        num_good_agents, num_adversaries, num_landmarks = 1, 3, 2
+        num_good_agents, num_adversaries, num_landmarks = self.counts
         world.agents = [Agent() for _ in range(num_adversaries + num_good_agents)]
         for i, agent in enumerate(world.agents):
             agent.name = 'agent %d' % i

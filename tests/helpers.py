@@ -18,6 +18,14 @@ CONFIGS = {
     "simple_reference": ("simple_reference", {}),
     "simple_crypto": ("simple_crypto", {}),
 }
+# entity-count variants the reference hard-codes away (no goldens; checked against the generic oracle)
+VARIANTS = {
+    "simple_tag_1v1": ("simple_tag", {"num_adversaries": 1, "num_good_agents": 1, "num_landmarks": 2}),
+    "simple_tag_2v1": ("simple_tag", {"num_adversaries": 2, "num_good_agents": 1, "num_landmarks": 2}),
+    "simple_tag_4v2": ("simple_tag", {"num_adversaries": 4, "num_good_agents": 2, "num_landmarks": 2}),
+    "simple_tag_6v2": ("simple_tag", {"num_adversaries": 6, "num_good_agents": 2, "num_landmarks": 3}),
+    "simple_adversary_n4": ("simple_adversary", {"num_agents": 4}),
+}
 NO_BENCHMARK = ("simple", "simple_push", "simple_speaker_listener", "simple_reference")
 
 
@@ -27,14 +35,14 @@ def load_golden(tag):
 
 def make_product_env(tag, **kw):
     from multiagent_particle_envs_b200 import make_env
-    name, skw = CONFIGS[tag]
+    name, skw = CONFIGS[tag] if tag in CONFIGS else VARIANTS[tag]
     kw.update(skw)
     return make_env(name, benchmark=(name not in NO_BENCHMARK), **kw)
 
 
 def descriptor(tag):
     from multiagent_particle_envs_b200 import scenarios
-    name, kw = CONFIGS[tag]
+    name, kw = CONFIGS[tag] if tag in CONFIGS else VARIANTS[tag]
     return scenarios.load(name).Scenario(**kw).make_world().descriptor()
 
 

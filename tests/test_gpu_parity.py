@@ -102,7 +102,8 @@ def test_golden_fixtures_free_running(tag):
 @pytest.mark.parametrize("tag,n", [("simple", 4096), ("simple_spread_n3", 8192), ("simple_spread_n6", 4096),
                                    ("simple_tag", 8192), ("simple_world_comm", 4096), ("simple_adversary", 4096),
                                    ("simple_push", 4096), ("simple_speaker_listener", 4096), ("simple_reference", 4096),
-                                   ("simple_crypto", 4096)])
+                                   ("simple_crypto", 4096), ("simple_tag_1v1", 2048), ("simple_tag_2v1", 2048),
+                                   ("simple_tag_4v2", 2048), ("simple_tag_6v2", 2048), ("simple_adversary_n4", 2048)])
 def test_seeded_worlds_vs_oracle(tag, n):
     from oracle import Oracle
     from multiagent_particle_envs_b200 import _lib
@@ -133,7 +134,7 @@ def test_seeded_worlds_vs_oracle(tag, n):
     fobs, frew, fdone, finfo = o32.observe(pv, lm, comm, flags, goal=goal)
     assert np.array_equal(obs, fobs)
     assert np.array_equal(done, fdone)
-    count_cols = [1, 3] if tag.startswith("simple_spread") else ([0] if tag in ("simple_tag", "simple_world_comm") else [])
+    count_cols = [1, 3] if tag.startswith("simple_spread") else ([0] if tag.startswith(("simple_tag", "simple_world_comm")) else [])
     for c in count_cols:                                              # collisions / occupied landmarks
         assert np.array_equal(info[:, :, c], finfo[:, :, c])
     np.testing.assert_allclose(rew, frew, rtol=2e-6, atol=2e-6)       # only expf ulps may differ
