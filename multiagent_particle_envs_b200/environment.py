@@ -157,6 +157,44 @@ class MultiAgentEnv(_Env):
         as_numpy = not hasattr(action_n[0], "dim")
         return self._pack_batched(nw, hout, as_numpy=as_numpy)
 
+    # ---- asynchronous stepping for host callers (batch extension) ------------------------------
+    def step_async(self, action_n):
+        """Enqueue H2D(actions) -> fused step -> D2H(outputs) on the current CUDA stream and return
+        immediately; the caller overlaps its own host work (or another env's step) with the transfers and
+        collects the results with `step_wait()`.  Host inputs only (NumPy / CPU tensors), batched mode."""
+        world = self.world
+        if not world.batched:
+            raise ValueError("step_async needs a batched env (make_env(..., num_envs=N))")
+        if getattr(self, "_pending", None) is not None:
+            raise RuntimeError("step_async called twice without step_wait")
+        nw = world.bind()
+        mode, payload = self._classify(action_n, nw)
+        if mode == "cuda":
+            raise ValueError("step_async is for host buffers; CUDA-tensor steps are already asynchronous")
+        hs = nw.host_staging()
+        ptrs = []
+        for i, a in enumerate(payload):
+            if mode == "pinned":
+                ptrs.append(a.data_ptr())
+            else:
+                hs["host_act"][i].copy_(a)
+                ptrs.append(hs["host_act"][i].data_ptr())
+        hout = nw.step_host(_lib.ptr_array(ptrs), self._flags(), with_info=self._native_info)
+        ev = nw.torch.cuda.Event()
+        ev.record(nw.torch.cuda.current_stream(nw.device))
+        self._pending = (hout, ev, payload, not hasattr(action_n[0], "dim"))
+        world._obs_valid = False
+
+    def step_wait(self):
+        """Block until the step enqueued by `step_async` has landed in host memory; returns what `step` returns."""
+        if getattr(self, "_pending", None) is None:
+            raise RuntimeError("step_wait without step_async")
+        hout, ev, _keepalive, as_numpy = self._pending
+        self._pending = None
+        ev.synchronize()
+        self._last_out = hout
+        return self._pack_batched(self.world.bind(), hout, as_numpy=as_numpy)
+
     # ---- input classification ---------------------------------------------------------------
     def _to_cpu_tensor(self, a, i):
         import torch

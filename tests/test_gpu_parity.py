@@ -305,3 +305,26 @@ def test_lane_per_agent_spread_kernel_is_bit_identical(tmp_path):
     assert set(res["0"]) == set(res["1"]) and len(res["0"]) == 8
     for k in res["0"]:
         assert np.array_equal(res["0"][k], res["1"][k]), k
+
+
+def test_step_async_matches_step_and_interleaves_two_envs():
+    """step_async / step_wait == step, and two envs can be in flight at once (the use case: overlap the
+    transfers of one batch with host work on another)"""
+    n = 4096
+    envs = [make_product_env("simple_tag", num_envs=n, seed=s) for s in (1, 2)]
+    refs = [make_product_env("simple_tag", num_envs=n, seed=s) for s in (1, 2)]
+    for e in envs + refs:
+        e.reset()
+    rng = np.random.RandomState(0)
+    for t in range(3):
+        acts = [[np.ascontiguousarray(a) for a in split_cols(random_actions(e.world.native.act_dims, n, rng).astype(np.float32),
+                                                             e.world.native.act_dims)] for e in envs]
+        for e, a in zip(envs, acts):
+            e.step_async(a)                       # both steps are enqueued before either is collected
+        outs = [e.step_wait() for e in envs]
+        for r, a, (obs_n, rew_n, done_n, info_n) in zip(refs, acts, outs):
+            ro, rr, rd, _ = r.step(a)
+            for x, y in zip(obs_n + rew_n, ro + rr):
+                assert isinstance(x, np.ndarray) and np.array_equal(x, y)
+    with pytest.raises(RuntimeError):
+        envs[0].step_wait()
