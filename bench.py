@@ -365,6 +365,25 @@ def run_b200_arm(args, rank, local_rank, world):
     e2e_total, e2e_max, _ = aggregate_counters(N_ENV * k_e2e, e2e_seconds)
     e2e_value = e2e_total / e2e_max
 
+    # extra (not the headline): two env batches in flight through step_async / step_wait, so that the upload +
+    # step of one overlaps the download of the other -- what a double-buffered host trainer would see
+    env_b = ring[1][0]
+    for b in range(2):
+        env.step_async(host_acts[b % 4]); env_b.step_async(host_acts[(b + 1) % 4]); env.step_wait(); env_b.step_wait()
+    torch.cuda.synchronize()
+    w0 = time.perf_counter()
+    env.step_async(host_acts[0])
+    for b in range(k_e2e):
+        nxt = env_b if b % 2 == 0 else env
+        cur = env if b % 2 == 0 else env_b
+        if b + 1 < k_e2e:
+            nxt.step_async(host_acts[(b + 1) % 4])
+        obs_n, rew_n, done_n, _ = cur.step_wait()
+        checksum += float(rew_n[0][0])
+    torch.cuda.synchronize()
+    pipe_seconds = time.perf_counter() - w0
+    pipe_total, pipe_max, _ = aggregate_counters(N_ENV * k_e2e, pipe_seconds)
+
     if rank == 0:
         peak, peak_src = measured_peak()
         launch_s = max_seconds / args.steps
@@ -387,6 +406,8 @@ def run_b200_arm(args, rank, local_rank, world):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": k_e2e, "ms_per_step": 1e3 * e2e_max / k_e2e, "api": "MultiAgentEnv.step(pinned host tensors)"},
+            "e2e_two_batches_in_flight": {"value": pipe_total / pipe_max, "unit": UNIT, "ms_per_step": 1e3 * pipe_max / k_e2e,
+                                          "api": "step_async / step_wait alternating over two env batches"},
             "gpu_launches": gpu_launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
