@@ -368,16 +368,21 @@ def run_b200_arm(args, rank, local_rank, world):
     # extra (not the headline): two env batches in flight through step_async / step_wait, so that the upload +
     # step of one overlaps the download of the other -- what a double-buffered host trainer would see
     env_b = ring[1][0]
+    lanes = {id(env): torch.cuda.Stream(dev), id(env_b): torch.cuda.Stream(dev)}   # one stream per env batch
+
+    def launch(e, acts):
+        with torch.cuda.stream(lanes[id(e)]):
+            e.step_async(acts)
+
     for b in range(2):
-        env.step_async(host_acts[b % 4]); env_b.step_async(host_acts[(b + 1) % 4]); env.step_wait(); env_b.step_wait()
+        launch(env, host_acts[b % 4]); launch(env_b, host_acts[(b + 1) % 4]); env.step_wait(); env_b.step_wait()
     torch.cuda.synchronize()
     w0 = time.perf_counter()
-    env.step_async(host_acts[0])
+    launch(env, host_acts[0])
     for b in range(k_e2e):
-        nxt = env_b if b % 2 == 0 else env
-        cur = env if b % 2 == 0 else env_b
+        cur, nxt = (env, env_b) if b % 2 == 0 else (env_b, env)
         if b + 1 < k_e2e:
-            nxt.step_async(host_acts[(b + 1) % 4])
+            launch(nxt, host_acts[(b + 1) % 4])
         obs_n, rew_n, done_n, _ = cur.step_wait()
         checksum += float(rew_n[0][0])
     torch.cuda.synchronize()
