@@ -4,7 +4,7 @@ scalar (batch-1, NumPy) convention for every scenario, benchmark_data shapes, go
 import numpy as np
 import pytest
 
-from helpers import CONFIGS, NO_BENCHMARK, descriptor, load_golden, make_product_env, random_actions, random_states, split_cols
+from helpers import CONFIGS, NO_BENCHMARK, load_golden, make_product_env, split_cols
 
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")

@@ -6,8 +6,7 @@ on the kernels' own stored state.  Run on the B200 box: pytest -m gpu."""
 import numpy as np
 import pytest
 
-from helpers import (CONFIGS, load_golden, make_product_env, random_actions, random_goals, random_states, split_cols,
-                     step_flags)
+from helpers import CONFIGS, load_golden, make_product_env, random_actions, random_goals, random_states, split_cols
 
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")

@@ -2,10 +2,9 @@
 oracle on everything would be slow): determinism, shard equivalence (the multi-GPU contract,
 SURVEY.md 8(e)), world-permutation equivariance, collaborative-reward structure, reset
 distributions and masked reset."""
-import numpy as np
 import pytest
 
-from helpers import make_product_env, random_actions
+from helpers import make_product_env
 
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
