@@ -130,6 +130,16 @@ class MultiAgentEnv(_Env):
         flags = self._flags()
         if self.discrete_action_input:
             action_n = self._onehot_from_indices(action_n)
+        if not world.batched and not any(hasattr(a, "dim") for a in action_n):
+            # scalar convention fast path: NumPy in, NumPy out, no tensor objects created per step
+            hs = nw.host_staging()
+            for i, a in enumerate(action_n):
+                np.copyto(hs["host_act_np"][i][0], np.asarray(a, dtype=np.float32).reshape(-1))
+            hout = nw.step_host(hs["host_act_ptrs"], flags, with_info=self._native_info)
+            nw.torch.cuda.current_stream(nw.device).synchronize()
+            self._last_out = hout
+            world._obs_valid = False
+            return self._pack_scalar(nw, hout)
         mode, payload = self._classify(action_n, nw)
         if mode == "cuda":
             out = nw.out if self.reuse_buffers else nw.new_outputs()
@@ -257,11 +267,15 @@ class MultiAgentEnv(_Env):
         return obs_n, reward_n, done_n, info_n
 
     def _pack_scalar(self, nw, hout):
-        obs_n = [o[0].detach().to("cpu").numpy().astype(np.float64) for o in hout.obs]
-        rew = hout.rew[:, 0].detach().to("cpu").numpy().astype(np.float64)
+        if getattr(hout, "obs_np", None) is not None:       # pinned host outputs: plain NumPy views
+            obs_n = [o[0].astype(np.float64) for o in hout.obs_np]
+            rew = hout.rew_np[:, 0].astype(np.float64)
+            done_n = [bool(d) for d in hout.done_np[:, 0]]
+        else:
+            obs_n = [o[0].detach().to("cpu").numpy().astype(np.float64) for o in hout.obs]
+            rew = hout.rew[:, 0].detach().to("cpu").numpy().astype(np.float64)
+            done_n = [bool(d) for d in hout.done[:, 0].detach().to("cpu")]
         reward_n = [rew[i] for i in range(self.n)]
-        done_host = hout.done[:, 0].detach().to("cpu")
-        done_n = [bool(done_host[i]) for i in range(self.n)]
         if self.done_callback is not None:
             done_n = [self.done_callback(agent, self.world) for agent in self.agents]
         info_n = {'n': self._info_list(nw, hout, False)}

@@ -92,6 +92,10 @@ class Outputs(object):
         self.rew_list = [self.rew[i] for i in range(A)]
         done_b = self.done.view(torch.bool)
         self.done_list = [done_b[i] for i in range(A)]
+        if pinned_host:   # NumPy views of the same pinned memory (scalar convention: no per-step tensor ops)
+            self.obs_np = [o.numpy() for o in self.obs]
+            self.rew_np, self.done_np = self.rew.numpy(), self.done.numpy()
+            self.info_np = self.info.numpy() if self.info is not None else None
         self.obs_ptrs = _lib.ptr_array([t.data_ptr() for t in self.obs])
         self.rew_ptr = self.rew.data_ptr()
         self.done_ptr = self.done.data_ptr()
@@ -194,7 +198,7 @@ class NativeWorld(ShapeHandle):
             host_act = [torch.zeros(N, ad, dtype=torch.float32).pin_memory() for ad in self.act_dims]
             dev_act = [torch.zeros(N, ad, dtype=torch.float32, device=self.device) for ad in self.act_dims]
             self._host = dict(
-                host_act=host_act, dev_act=dev_act,
+                host_act=host_act, dev_act=dev_act, host_act_np=[t.numpy() for t in host_act],
                 host_act_ptrs=_lib.ptr_array([t.data_ptr() for t in host_act]),
                 dev_act_ptrs=_lib.ptr_array([t.data_ptr() for t in dev_act]),
                 host_out=[Outputs(self, pinned_host=True), Outputs(self, pinned_host=True)], flip=0)
@@ -235,7 +239,8 @@ class NativeWorld(ShapeHandle):
             if sc == _lib.SCN_CRYPTO:           # (agent.state.c, goal colour)
                 return (info[0:C].t(), info[C:2 * C].t())
             return info[0]
-        v = info[:, 0].detach().to("cpu").numpy().astype(np.float64)
+        v = (out.info_np[i, :, 0] if getattr(out, "info_np", None) is not None
+             else info[:, 0].detach().to("cpu").numpy()).astype(np.float64)
         if sc == _lib.SCN_SPREAD:
             return (float(v[0]), int(v[1]), float(v[2]), int(v[3]))
         if sc == _lib.SCN_ADVERSARY:
