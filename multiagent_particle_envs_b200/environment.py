@@ -294,7 +294,7 @@ class MultiAgentEnv(_Env):
         self._reset_render()
         self.agents = world.policy_agents
         out = nw.out if (self.reuse_buffers or not world.batched) else nw.new_outputs()
-        nw.observe(out, 0)
+        nw.observe(out, 0, with_info=False)
         world._obs_valid = False
         if world.batched:
             return list(out.obs)

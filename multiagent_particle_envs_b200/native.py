@@ -102,6 +102,32 @@ class Outputs(object):
         self.info_ptr = self.info.data_ptr() if self.info is not None else None
 
 
+class FreshOutputs(object):
+    """Per-step device outputs for callers that keep what `step` returns (the reference hands out freshly
+    allocated arrays).  Same attributes as `Outputs`, built with as few tensor operations as possible -- one
+    float slab carved with as_strided, `unbind` for the per-agent views -- because at ~6 us per kernel the
+    host-side cost of a step is what a GPU-resident trainer actually waits for."""
+
+    def __init__(self, nw):
+        import torch
+        N, A = nw.n_env, nw.n_agents
+        lay = nw._fresh_layout
+        fs = torch.empty(lay["words"], dtype=torch.float32, device=nw.device)
+        self.slab = fs
+        self.obs = [fs.as_strided((N, od), (od, 1), off) for off, od in lay["obs"]]
+        self.rew = fs.as_strided((A, N), (N, 1), lay["rew"])
+        self.rew_list = self.rew.unbind(0)
+        self.info = fs.as_strided((A, nw.info_dim, N), (nw.info_dim * N, N, 1), lay["info"]) if nw.info_dim > 0 else None
+        done_b = torch.empty((A, N), dtype=torch.bool, device=nw.device)   # written as 0/1 bytes by the kernel
+        self.done = done_b.view(torch.uint8)
+        self.done_list = done_b.unbind(0)
+        base = fs.data_ptr()
+        self.obs_ptrs = _lib.ptr_array([base + 4 * off for off, _ in lay["obs"]])
+        self.rew_ptr = base + 4 * lay["rew"]
+        self.done_ptr = done_b.data_ptr()
+        self.info_ptr = base + 4 * lay["info"] if nw.info_dim > 0 else None
+
+
 class NativeWorld(ShapeHandle):
     def __init__(self, desc, n_env, device=None, seed=0, world_offset=0):
         import torch
@@ -130,6 +156,16 @@ class NativeWorld(ShapeHandle):
         self.seed = int(seed)
         self.world_offset = int(world_offset)
         self.epoch = 0
+        # layout of FreshOutputs' float slab, in 4-byte words (every part 64-word = 256-byte aligned)
+        off, obs_l = 0, []
+        for od in self.obs_dims:
+            obs_l.append((off, od))
+            off = _align(off + N * od, 64)
+        rew_off = off
+        off = _align(off + A * N, 64)
+        info_off = off
+        off = _align(off + A * self.info_dim * N, 64)
+        self._fresh_layout = dict(obs=obs_l, rew=rew_off, info=info_off, words=max(off, 64))
         self.out = Outputs(self)           # persistent outputs (observe(), reuse mode)
         self._host = None                  # lazily created staging for host callers
         self._has_comm = NC > 0
@@ -145,7 +181,7 @@ class NativeWorld(ShapeHandle):
                 self.goal.data_ptr() if self._has_goal else None)
 
     def new_outputs(self):
-        return Outputs(self)
+        return FreshOutputs(self)
 
     # ---- reset -------------------------------------------------------------------------------
     def reset(self, mask=None):
