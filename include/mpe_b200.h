@@ -56,6 +56,9 @@ enum mpe_scenario {
     MPE_SCN_SPEAKER_LISTENER = 6, /* simple_speaker_listener.py */
     MPE_SCN_REFERENCE = 7,        /* simple_reference.py */
     MPE_SCN_CRYPTO = 8,           /* simple_crypto.py */
+    MPE_SCN_CUSTOM = 9,           /* user scenario: native _set_action + World.step for ANY entity table (<= 8 agents,
+                                     <= 8 landmarks); observation / reward stay in the caller's (GPU) code, so only
+                                     mpe_set_action, mpe_world_step and mpe_reset are available */
     MPE_SCN_COUNT_
 };
 

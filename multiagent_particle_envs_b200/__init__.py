@@ -11,7 +11,7 @@ and does not need gym.  There is no CPU fallback: stepping a world requires the 
 from .core import World, Agent, Landmark, Entity, EntityState, AgentState, Action  # noqa: F401
 from .environment import MultiAgentEnv  # noqa: F401
 from .multi_discrete import MultiDiscrete  # noqa: F401
-from .scenario import BaseScenario, NativeScenario  # noqa: F401
+from .scenario import BaseScenario, NativeScenario, TorchScenario  # noqa: F401
 from .make_env import make_env  # noqa: F401
 
 __version__ = "0.1.0"

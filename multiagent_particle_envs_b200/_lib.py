@@ -16,7 +16,7 @@ MPE_MAX_LANDMARKS = 8
 
 # enum mpe_scenario
 SCN_SIMPLE, SCN_SPREAD, SCN_TAG, SCN_WORLD_COMM, SCN_ADVERSARY, SCN_PUSH, SCN_SPEAKER_LISTENER, \
-    SCN_REFERENCE, SCN_CRYPTO = range(9)
+    SCN_REFERENCE, SCN_CRYPTO, SCN_CUSTOM = range(10)
 
 # enum mpe_step_flags
 FLAG_SHARED_REWARD = 1

@@ -28,6 +28,7 @@ _PROGRAM_IDS = {
     "simple_speaker_listener": _lib.SCN_SPEAKER_LISTENER,
     "simple_reference": _lib.SCN_REFERENCE,
     "simple_crypto": _lib.SCN_CRYPTO,
+    "custom": _lib.SCN_CUSTOM,     # user scenario: native physics, observation / reward in the user's torch code
 }
 
 
@@ -185,9 +186,10 @@ class World(object):
         """Flatten what make_world() wrote onto this object into the C-ABI `mpe_desc`."""
         if self.native_program not in _PROGRAM_IDS:
             raise NotImplementedError(
-                "World has no native sm_100a scenario program (world.native_program=%r). Only the built-in "
-                "scenarios are compiled; arbitrary Python reward/observation callbacks cannot run on the "
-                "device and there is deliberately no CPU fallback." % (self.native_program,))
+                "World has no native sm_100a scenario program (world.native_program=%r). The built-in scenarios "
+                "are compiled; a user scenario must derive from TorchScenario (native physics, observation / "
+                "reward written with torch ops on the device). There is deliberately no CPU fallback."
+                % (self.native_program,))
         if self.scripted_agents:
             raise NotImplementedError("scripted agents (action_callback) are not supported by the native path")
         if self.dim_p != 2:

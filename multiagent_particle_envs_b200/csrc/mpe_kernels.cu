@@ -330,6 +330,107 @@ __global__ void __launch_bounds__(kMaxThreads, MPE_MIN_BLOCKS) mpe_kernel(const 
     }
 }
 
+// ---- generic program for user scenarios (MPE_SCN_CUSTOM) ------------------------------------------
+// Any entity table, flags read at run time; same arithmetic primitives and the same (a, b) pair order as
+// the compiled programs, so for a table that matches a built-in scenario the state is bit-identical.
+// Loops are unrolled to the maximum counts with run-time guards, which keeps every array in registers.
+__global__ void __launch_bounds__(128) generic_set_action_kernel(const __grid_constant__ StepArgs a) {
+    const int64_t w = a.begin + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (w >= a.begin + a.count) return;
+    const DevDesc &d = a.d;
+    const int64_t n = a.n;
+    const int C = d.g_dim_c;
+#pragma unroll
+    for (int i = 0; i < kMaxA; ++i) {
+        if (i >= d.g_agents) break;
+        const bool movable = (d.g_movable >> i) & 1u, silent = (d.g_silent >> i) & 1u;
+        const int adim = (movable ? 5 : 0) + (silent ? 0 : C);
+        const float *row = a.act[i] + w * adim;
+        float x = 0.0f, y = 0.0f;
+        int off = 0;
+        if (movable) {                                             // environment.py:157-181
+            float p0 = row[0], p1 = row[1], p2 = row[2], p3 = row[3], p4 = row[4];
+            if (a.flags & MPE_FLAG_FORCE_DISCRETE_ACTION) {
+                int best = 0;
+                float bv = p0;
+                if (p1 > bv) { bv = p1; best = 1; }
+                if (p2 > bv) { bv = p2; best = 2; }
+                if (p3 > bv) { bv = p3; best = 3; }
+                if (p4 > bv) { bv = p4; best = 4; }
+                p1 = best == 1 ? 1.0f : 0.0f; p2 = best == 2 ? 1.0f : 0.0f;
+                p3 = best == 3 ? 1.0f : 0.0f; p4 = best == 4 ? 1.0f : 0.0f;
+            }
+            x = __fmul_rn(p1 - p2, d.a_sens[i]);
+            y = __fmul_rn(p3 - p4, d.a_sens[i]);
+            off = 5;
+        }
+        a.u[i * n + w] = make_float2(x, y);
+        if (!silent)                                               // environment.py:183-190
+            for (int q = 0; q < C; ++q) a.c[(d.g_slot[i] * C + q) * n + w] = row[off + q];
+    }
+}
+
+__global__ void __launch_bounds__(128) generic_world_step_kernel(const __grid_constant__ StepArgs a) {
+    const int64_t w = a.begin + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (w >= a.begin + a.count) return;
+    const DevDesc &d = a.d;
+    const int64_t n = a.n;
+    const int A = d.g_agents, L = d.g_landmarks, C = d.g_dim_c;
+    float px[kMaxA], py[kMaxA], vx[kMaxA], vy[kMaxA], fx[kMaxA], fy[kMaxA], lx[kMaxL], ly[kMaxL];
+#pragma unroll
+    for (int i = 0; i < kMaxA; ++i) {
+        px[i] = py[i] = vx[i] = vy[i] = fx[i] = fy[i] = 0.0f;
+        if (i < A) {
+            const float4 v = a.pv[i * n + w];
+            const float2 u = a.u[i * n + w];
+            px[i] = v.x; py[i] = v.y; vx[i] = v.z; vy[i] = v.w;
+            fx[i] = u.x; fy[i] = u.y;                               // apply_action_force (core.py:134-140)
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < kMaxL; ++l) {
+        lx[l] = ly[l] = 0.0f;
+        if (l < L) {
+            const float2 v = a.lm[l * n + w];
+            lx[l] = v.x; ly[l] = v.y;
+        }
+    }
+    // apply_environment_force (core.py:143-155), pairs (a, b), a < b, agents then landmarks
+#pragma unroll
+    for (int i = 0; i < kMaxA; ++i) {
+        if (i >= A || !((d.g_collide >> i) & 1u)) continue;
+#pragma unroll
+        for (int j = i + 1; j < kMaxA; ++j) {
+            if (j >= A || !((d.g_collide >> j) & 1u)) continue;
+            const float2 f = pair_force(__fsub_rn(px[i], px[j]), __fsub_rn(py[i], py[j]), __fadd_rn(d.a_size[i], d.a_size[j]),
+                                        d.contact_force, d.contact_margin, d.inv_margin);
+            if ((d.g_movable >> i) & 1u) { fx[i] = __fadd_rn(fx[i], f.x); fy[i] = __fadd_rn(fy[i], f.y); }
+            if ((d.g_movable >> j) & 1u) { fx[j] = __fsub_rn(fx[j], f.x); fy[j] = __fsub_rn(fy[j], f.y); }
+        }
+#pragma unroll
+        for (int l = 0; l < kMaxL; ++l) {
+            if (l >= L || !((d.g_lcollide >> l) & 1u)) continue;
+            const float2 f = pair_force(__fsub_rn(px[i], lx[l]), __fsub_rn(py[i], ly[l]), __fadd_rn(d.a_size[i], d.l_size[l]),
+                                        d.contact_force, d.contact_margin, d.inv_margin);
+            if ((d.g_movable >> i) & 1u) { fx[i] = __fadd_rn(fx[i], f.x); fy[i] = __fadd_rn(fy[i], f.y); }
+        }
+    }
+    // integrate_state (core.py:158-169)
+#pragma unroll
+    for (int i = 0; i < kMaxA; ++i) {
+        if (i >= A || !((d.g_movable >> i) & 1u)) continue;
+        float4 r;
+        if (d.a_max_speed[i] >= 0.0f)
+            r = integrate_entity<true>(px[i], py[i], vx[i], vy[i], fx[i], fy[i], d.keep, d.a_dt_over_mass[i], d.dt, d.a_max_speed[i]);
+        else
+            r = integrate_entity<false>(px[i], py[i], vx[i], vy[i], fx[i], fy[i], d.keep, d.a_dt_over_mass[i], d.dt, 0.0f);
+        a.pv[i * n + w] = r;
+    }
+    // update_agent_state (core.py:171-177): state.c = action.c for the speakers
+    for (int q = 0; q < d.g_comm_rows; ++q) a.comm[q * n + w] = a.c[q * n + w];
+    (void)C;
+}
+
 // ---- reset: i.i.d. uniform positions (e.g. simple_spread.py:38-45) -----------------------------
 struct ResetArgs {
     int64_t n;
@@ -407,6 +508,17 @@ static Program make_program() {
     return p;
 }
 
+// MPE_SCN_CUSTOM: shapes come from the descriptor at create time (see mpe_create)
+static Program make_generic_program() {
+    Program p{};
+    p.scenario = MPE_SCN_CUSTOM;
+    p.validate = [](const mpe_desc &) { return true; };
+    p.fn[kSetAction] = generic_set_action_kernel;
+    p.fn[kWorldStep] = generic_world_step_kernel;
+    p.smem_bytes = 0;
+    return p;
+}
+
 template <int N>
 static Program make_spread_program() {
     Program p = make_program<Spread<N>>();
@@ -418,6 +530,7 @@ static Program make_spread_program() {
 
 static const Program *programs(int *count) {
     static const Program table[] = {
+        make_generic_program(),
         make_program<Simple<1, 1>>(),
         make_spread_program<2>(), make_spread_program<3>(), make_spread_program<4>(),
         make_spread_program<5>(), make_spread_program<6>(),
@@ -452,6 +565,7 @@ static_assert(sizeof(mpe_desc) == 480, "mpe_desc layout is part of the ABI (mirr
 struct mpe_env {
     mpe_desc desc;
     DevDesc dev;
+    Program custom;        // MPE_SCN_CUSTOM: the generic program with this handle's shapes
     const Program *prog;
     int64_t n;
     int device;
@@ -500,8 +614,9 @@ extern "C" int mpe_create(const mpe_desc *desc, int64_t n_env, int device, mpe_h
         CUDA_TRY(cudaGetDevice(&prev));
         CUDA_TRY(cudaSetDevice(device));
         for (int m = 0; m < 4; ++m)
-            CUDA_TRY(cudaFuncSetAttribute(prog->fn[m], cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          prog->smem_bytes * max_warps_per_block(prog->smem_bytes)));
+            if (prog->fn[m] && prog->smem_bytes > 0)
+                CUDA_TRY(cudaFuncSetAttribute(prog->fn[m], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              prog->smem_bytes * max_warps_per_block(prog->smem_bytes)));
         if (prog->lanes_fn)
             CUDA_TRY(cudaFuncSetAttribute(prog->lanes_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, prog->lanes_smem * 4));
         CUDA_TRY(cudaSetDevice(prev));
@@ -524,6 +639,17 @@ extern "C" int mpe_create(const mpe_desc *desc, int64_t n_env, int device, mpe_h
     }
     h->desc = *desc;
     h->prog = prog;
+    if (desc->scenario == MPE_SCN_CUSTOM) {   // shapes of a user scenario come from its descriptor
+        h->custom = *prog;
+        Program &c = h->custom;
+        c.A = desc->n_agents; c.L = desc->n_landmarks; c.DIMC = desc->dim_c; c.INFO = 0; c.G = 0; c.NS = 0;
+        for (int i = 0; i < c.A; ++i) {
+            c.NS += desc->agent_silent[i] ? 0 : 1;
+            c.act_dim[i] = (desc->agent_movable[i] ? 5 : 0) + (desc->agent_silent[i] ? 0 : desc->dim_c);
+            c.obs_dim[i] = 0;   // defined by the caller's observation code
+        }
+        h->prog = &h->custom;
+    }
     h->n = n_env;
     h->device = device;
     DevDesc &d = h->dev;
@@ -540,6 +666,17 @@ extern "C" int mpe_create(const mpe_desc *desc, int64_t n_env, int device, mpe_h
         d.a_max_speed[i] = desc->agent_max_speed[i] < 0 ? -1.0f : static_cast<float>(desc->agent_max_speed[i]);
     }
     for (int l = 0; l < desc->n_landmarks; ++l) d.l_size[l] = static_cast<float>(desc->landmark_size[l]);
+    d.g_agents = desc->n_agents; d.g_landmarks = desc->n_landmarks; d.g_dim_c = desc->dim_c;
+    int slot = 0;
+    for (int i = 0; i < desc->n_agents; ++i) {
+        if (desc->agent_movable[i]) d.g_movable |= 1u << i;
+        if (desc->agent_collide[i]) d.g_collide |= 1u << i;
+        if (desc->agent_silent[i]) d.g_silent |= 1u << i;
+        d.g_slot[i] = desc->agent_silent[i] ? static_cast<int8_t>(-1) : static_cast<int8_t>(slot++);
+    }
+    for (int l = 0; l < desc->n_landmarks; ++l)
+        if (desc->landmark_collide[l]) d.g_lcollide |= 1u << l;
+    d.g_comm_rows = slot * desc->dim_c;
     *out = h;
     return MPE_OK;
 }
@@ -557,7 +694,10 @@ extern "C" int mpe_destroy(mpe_handle h) {
 
 extern "C" int mpe_num_agents(mpe_handle h) { return h ? h->prog->A : MPE_ERR_BAD_ARG; }
 extern "C" int64_t mpe_num_envs(mpe_handle h) { return h ? h->n : MPE_ERR_BAD_ARG; }
-extern "C" int mpe_obs_dim(mpe_handle h, int i) { return (h && i >= 0 && i < h->prog->A) ? h->prog->obs_dim[i] : MPE_ERR_BAD_ARG; }
+extern "C" int mpe_obs_dim(mpe_handle h, int i) {
+    if (!h || i < 0 || i >= h->prog->A) return MPE_ERR_BAD_ARG;
+    return h->prog->scenario == MPE_SCN_CUSTOM ? MPE_ERR_UNSUPPORTED : h->prog->obs_dim[i];
+}
 extern "C" int mpe_act_dim(mpe_handle h, int i) { return (h && i >= 0 && i < h->prog->A) ? h->prog->act_dim[i] : MPE_ERR_BAD_ARG; }
 extern "C" int mpe_num_speakers(mpe_handle h) { return h ? h->prog->NS : MPE_ERR_BAD_ARG; }
 extern "C" int mpe_num_goals(mpe_handle h) { return h ? h->prog->G : MPE_ERR_BAD_ARG; }
@@ -604,6 +744,20 @@ static int launch(mpe_handle h, int mode, StepArgs &args, void *stream, int64_t 
                                          static_cast<cudaStream_t>(stream));
         if (prev != h->device) cudaSetDevice(prev);
         if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernel(spread_lanes)");
+        __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED);
+        return MPE_OK;
+    }
+    if (h->prog->scenario == MPE_SCN_CUSTOM) {   // generic program: one thread per world, no staging
+        if (h->prog->fn[mode] == nullptr) return MPE_ERR_UNSUPPORTED;
+        int prev = 0;
+        CUDA_TRY(cudaGetDevice(&prev));
+        if (prev != h->device) CUDA_TRY(cudaSetDevice(h->device));
+        void *params[] = {&args};
+        cudaError_t e = cudaLaunchKernel(reinterpret_cast<const void *>(h->prog->fn[mode]),
+                                         dim3(static_cast<unsigned>((args.count + 127) / 128)), dim3(128), params, 0,
+                                         static_cast<cudaStream_t>(stream));
+        if (prev != h->device) cudaSetDevice(prev);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernel(generic)");
         __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED);
         return MPE_OK;
     }
@@ -709,6 +863,7 @@ extern "C" int mpe_world_step(mpe_handle h, void *pv, const void *lm, float *com
 extern "C" int mpe_observe(mpe_handle h, const void *pv, const void *lm, const float *comm, const int32_t *goal,
                            float *const *obs_n, float *rew, uint8_t *done, float *info, uint32_t flags, void *stream) {
     if (!h) return MPE_ERR_BAD_ARG;
+    if (h->prog->scenario == MPE_SCN_CUSTOM) return MPE_ERR_UNSUPPORTED;
     StepArgs a{};
     int r = fill_state(h, a, const_cast<void *>(pv), lm, const_cast<float *>(comm), goal);
     if (r) return r;
@@ -755,6 +910,7 @@ static int issue_copies(CopySeg *seg, int n, cudaMemcpyKind kind, cudaStream_t s
 static int step_range(mpe_handle h, void *pv, const void *lm, float *comm, const int32_t *goal,
                       const float *const *act_n, float *const *obs_n, float *rew, uint8_t *done, float *info,
                       uint32_t flags, void *stream, int64_t begin, int64_t count) {
+    if (h->prog->scenario == MPE_SCN_CUSTOM) return MPE_ERR_UNSUPPORTED;
     StepArgs a{};
     int r = fill_state(h, a, pv, lm, comm, goal);
     if (r) return r;

@@ -53,9 +53,12 @@ class MultiAgentEnv(_Env):
         #: returning freshly allocated ones (zero allocations per step; outputs alias across steps)
         self.reuse_buffers = False
 
+        self._custom = (getattr(world, "native_program", None) == "custom")
+        if self._custom and not world.batched:
+            raise NotImplementedError("user scenarios (TorchScenario) run in batched mode only: pass num_envs")
         for name, cb in (("reward_callback", reward_callback), ("observation_callback", observation_callback)):
             owner = getattr(cb, "__self__", None)
-            if cb is not None and not isinstance(owner, NativeScenario):
+            if cb is not None and not self._custom and not isinstance(owner, NativeScenario):
                 raise NotImplementedError(
                     "%s is an arbitrary Python callable; only scenarios with a compiled sm_100a program "
                     "(subclasses of NativeScenario) can be stepped, and there is no CPU fallback" % name)
@@ -78,8 +81,12 @@ class MultiAgentEnv(_Env):
                 self.action_space.append(MultiDiscrete([[0, sp.n - 1] for sp in total_action_space]))
             else:
                 self.action_space.append(total_action_space[0])
-            self.observation_space.append(spaces.Box(low=-np.inf, high=+np.inf, shape=(shapes.obs_dims[i],),
-                                                     dtype=np.float32))
+            if self._custom:   # as the reference does (environment.py:68): ask the callback (binds the batch: needs the GPU)
+                world.bind()
+                obs_dim = int(observation_callback(agent, world).shape[-1])
+            else:
+                obs_dim = shapes.obs_dims[i]
+            self.observation_space.append(spaces.Box(low=-np.inf, high=+np.inf, shape=(obs_dim,), dtype=np.float32))
         self._act_dims = list(shapes.act_dims)
         self._sub_sizes = [([5] if a.movable else []) + ([world.dim_c] if not a.silent else []) for a in self.agents]
 
@@ -130,6 +137,8 @@ class MultiAgentEnv(_Env):
         flags = self._flags()
         if self.discrete_action_input:
             action_n = self._onehot_from_indices(action_n)
+        if self._custom:
+            return self._step_custom(action_n, nw, flags)
         if not world.batched and not any(hasattr(a, "dim") for a in action_n):
             # scalar convention fast path: NumPy in, NumPy out, no tensor objects created per step
             hs = nw.host_staging()
@@ -166,6 +175,30 @@ class MultiAgentEnv(_Env):
             return self._pack_scalar(nw, hout)
         as_numpy = not hasattr(action_n[0], "dim")
         return self._pack_batched(nw, hout, as_numpy=as_numpy)
+
+    # ---- user scenarios: native _set_action + World.step, callbacks in the user's torch code -------
+    def _step_custom(self, action_n, nw, flags):
+        import torch
+        world = self.world
+        acts = []
+        for i, a in enumerate(action_n):
+            t = a if torch.is_tensor(a) else torch.as_tensor(np.asarray(a, dtype=np.float32))
+            t = t.to(device=nw.device, dtype=torch.float32).reshape(nw.n_env, self._act_dims[i]).contiguous()
+            acts.append(t)
+        nw.set_action(_lib.ptr_array([t.data_ptr() for t in acts]), flags)      # environment.py:87-88
+        world.step()                                                            # :90
+        obs_n = [self._get_obs(agent) for agent in self.agents]                 # :92-97
+        reward_n = [torch.as_tensor(self._get_reward(agent), device=nw.device, dtype=torch.float32).expand(nw.n_env)
+                    for agent in self.agents]
+        if self.done_callback is None:
+            done_n = [torch.zeros(nw.n_env, dtype=torch.bool, device=nw.device) for _ in self.agents]
+        else:
+            done_n = [self.done_callback(agent, world) for agent in self.agents]
+        info_n = {'n': [self._get_info(agent) for agent in self.agents]}
+        if self.shared_reward:                                                  # :100-102
+            total = torch.stack(reward_n).sum(0)
+            reward_n = [total] * self.n
+        return obs_n, reward_n, done_n, info_n
 
     # ---- asynchronous stepping for host callers (batch extension) ------------------------------
     def step_async(self, action_n):
@@ -293,6 +326,8 @@ class MultiAgentEnv(_Env):
             self.reset_callback(world, mask=mask, seed=seed)
         self._reset_render()
         self.agents = world.policy_agents
+        if self._custom:
+            return [self._get_obs(agent) for agent in self.agents]
         out = nw.out if (self.reuse_buffers or not world.batched) else nw.new_outputs()
         nw.observe(out, 0, with_info=False)
         world._obs_valid = False

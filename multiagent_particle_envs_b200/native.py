@@ -32,7 +32,8 @@ class ShapeHandle(object):
         self.n_agents = lib.mpe_num_agents(h)
         self.n_landmarks = int(desc.n_landmarks)
         self.dim_c = int(desc.dim_c)
-        self.obs_dims = [lib.mpe_obs_dim(h, i) for i in range(self.n_agents)]
+        self.custom = int(desc.scenario) == _lib.SCN_CUSTOM     # observation / reward live in the user's torch code
+        self.obs_dims = [] if self.custom else [lib.mpe_obs_dim(h, i) for i in range(self.n_agents)]
         self.act_dims = [lib.mpe_act_dim(h, i) for i in range(self.n_agents)]
         self.n_speakers = lib.mpe_num_speakers(h)
         self.n_goals = lib.mpe_num_goals(h)
@@ -166,7 +167,7 @@ class NativeWorld(ShapeHandle):
         info_off = off
         off = _align(off + A * self.info_dim * N, 64)
         self._fresh_layout = dict(obs=obs_l, rew=rew_off, info=info_off, words=max(off, 64))
-        self.out = Outputs(self)           # persistent outputs (observe(), reuse mode)
+        self.out = None if self.custom else Outputs(self)   # persistent outputs (observe(), reuse mode)
         self._host = None                  # lazily created staging for host callers
         self._has_comm = NC > 0
         self._has_goal = self.n_goals > 0

@@ -21,9 +21,7 @@ class BaseScenario(object):
         raise NotImplementedError()
 
 
-class NativeScenario(BaseScenario):
-    """Shared implementation of the callback surface for scenarios that have a native program."""
-
+class _BatchedScenario(BaseScenario):
     def _finish_world(self, world, num_envs=None, device=None):
         world.native_program = self.native_program
         world.scenario = self
@@ -37,6 +35,22 @@ class NativeScenario(BaseScenario):
         """i.i.d. uniform positions, zero velocity and comm (e.g. simple_spread.py:31-45) for the
         worlds selected by `mask` (all when None), drawn on the device from a Philox stream."""
         world.reset_states(mask=mask, seed=seed)
+
+
+class TorchScenario(_BatchedScenario):
+    """User-defined scenario.  `make_world()` fills the entity table exactly as in the reference (any mix of
+    movable / colliding / silent agents and landmarks, up to 8 + 8, end it with `return self._finish_world(world,
+    num_envs, device)`); `_set_action` and `World.step` then run on the generic native program, and the scenario's
+    own `observation(agent, world)` / `reward(agent, world)` (optionally `benchmark_data`, and a `done` callback) are
+    written with torch operations over the batched state: in a batched world `agent.state.p_pos`, `p_vel`, `c` and
+    `landmark.state.p_pos` are CUDA tensors of shape [num_envs, 2] (or [num_envs, dim_c]); return [num_envs, obs_dim]
+    and [num_envs].  Nothing runs on the CPU: the callbacks are vectorised over worlds on the GPU.  Batched mode
+    only (`make_env(..., num_envs=N)` / `make_world(num_envs=N)`)."""
+    native_program = "custom"
+
+
+class NativeScenario(_BatchedScenario):
+    """Shared implementation of the callback surface for scenarios that have a native program."""
 
     def observation(self, agent, world):
         return world.native_observation(agent)
