@@ -214,3 +214,32 @@ def test_headless_rasteriser_draws_circles():
     assert tuple(img[10, 10]) == (255, 255, 255)
     area = (img[:, :, 1] == 0).sum() / 700.0 ** 2 * 4.0           # red disc area in world units
     assert abs(area - np.pi * 0.2 ** 2) < 0.003
+
+
+def test_custom_scenario_descriptor_and_shape_only_handle():
+    """MPE_SCN_CUSTOM: any entity table is accepted; shapes come from the descriptor; observe / fused step are refused"""
+    from multiagent_particle_envs_b200 import Agent, Landmark, TorchScenario, World, _lib
+
+    class Scenario(TorchScenario):
+        def make_world(self, num_envs=None, device=None):
+            world = World()
+            world.dim_c = 4
+            world.agents = [Agent() for _ in range(7)]
+            for i, ag in enumerate(world.agents):
+                ag.name, ag.silent, ag.movable, ag.collide = 'agent %d' % i, i % 3 != 0, i != 6, i % 2 == 0
+            world.landmarks = [Landmark() for _ in range(8)]
+            return self._finish_world(world, num_envs, device)
+
+    world = Scenario().make_world(num_envs=64)
+    d = world.descriptor()
+    assert d.scenario == _lib.SCN_CUSTOM and d.n_agents == 7 and d.n_landmarks == 8
+    sh = world.native_shapes()
+    assert sh.custom and sh.obs_dims == [] and sh.n_speakers == 3
+    assert sh.act_dims == [9, 5, 5, 9, 5, 5, 4]
+    lib = _lib.load()
+    assert lib.mpe_obs_dim(sh.handle, 0) == _lib.ERR_UNSUPPORTED
+    assert lib.mpe_observe(sh.handle, 16, 16, 16, None, None, 16, 16, None, 0, None) == _lib.ERR_UNSUPPORTED
+    world.agents.append(Agent())
+    world.agents.append(Agent())
+    with pytest.raises(ValueError):          # more than 8 agents
+        world.descriptor()
