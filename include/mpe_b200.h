@@ -145,6 +145,12 @@ MPE_API int mpe_reset(mpe_handle h, void *agent_pv_dev, void *lm_p_dev, float *c
               const uint8_t *mask_dev, uint64_t seed, uint64_t world_offset, uint64_t epoch,
               void *stream);
 
+/* Same reset, but the epoch is read from device memory (*epoch_dev) and incremented afterwards on the stream:
+ * a reset captured in a CUDA graph then draws fresh initial conditions on every replay. */
+MPE_API int mpe_reset_dev_epoch(mpe_handle h, void *agent_pv_dev, void *lm_p_dev, float *comm_dev, int32_t *goal_dev,
+                                const uint8_t *mask_dev, uint64_t seed, uint64_t world_offset,
+                                unsigned long long *epoch_dev, void *stream);
+
 /* ---- the hot path ------------------------------------------------------------------------ */
 
 /* MultiAgentEnv._set_action for all agents (environment.py:144-192): act_n -> action.u, action.c.

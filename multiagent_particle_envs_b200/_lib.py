@@ -78,6 +78,7 @@ _SIGNATURES = {
     "mpe_info_dim": (ctypes.c_int, [_P]),
     "mpe_bytes_per_env_step": (ctypes.c_int64, [_P]),
     "mpe_reset": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, _P]),
+    "mpe_reset_dev_epoch": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, ctypes.c_uint64, ctypes.c_uint64, _P, _P]),
     "mpe_set_action": (ctypes.c_int, [_P, _PP, _P, _P, ctypes.c_uint32, _P]),
     "mpe_world_step": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "mpe_observe": (ctypes.c_int, [_P, _P, _P, _P, _P, _PP, _P, _P, _P, ctypes.c_uint32, _P]),

@@ -441,6 +441,7 @@ struct ResetArgs {
     int32_t *goal;
     const uint8_t *mask;
     uint64_t seed, world_offset, epoch;
+    const unsigned long long *epoch_dev;   // when non-null the epoch is read from device memory
     float agent_range, landmark_range[kMaxL];
     int goal_mod[4];
 };
@@ -449,13 +450,14 @@ __global__ void __launch_bounds__(256) reset_kernel(const __grid_constant__ Rese
     const int64_t w = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (w >= a.n) return;
     if (a.mask != nullptr && a.mask[w] == 0) return;
+    const uint64_t epoch = a.epoch_dev ? *a.epoch_dev : a.epoch;
     const uint64_t gw = a.world_offset + static_cast<uint64_t>(w);
     const uint2 key = make_uint2(static_cast<uint32_t>(a.seed), static_cast<uint32_t>(a.seed >> 32));
     // one Philox block = 4 x 32 bits = two entities' (x, y); counter = (world lo, world hi, epoch, block)
     const int E = a.A + a.L;
     for (int e = 0; e < E; e += 2) {
         const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(gw), static_cast<uint32_t>(gw >> 32),
-                                                 static_cast<uint32_t>(a.epoch), static_cast<uint32_t>(e >> 1)), key);
+                                                 static_cast<uint32_t>(epoch), static_cast<uint32_t>(e >> 1)), key);
         const uint32_t bits[4] = {r.x, r.y, r.z, r.w};
         for (int k = 0; k < 2 && e + k < E; ++k) {
             const int ent = e + k;
@@ -473,11 +475,13 @@ __global__ void __launch_bounds__(256) reset_kernel(const __grid_constant__ Rese
     for (int q = 0; q < a.NC; ++q) a.comm[q * a.n + w] = 0.0f;
     if (a.G > 0) {
         const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(gw), static_cast<uint32_t>(gw >> 32),
-                                                 static_cast<uint32_t>(a.epoch), 0x80000000u), key);
+                                                 static_cast<uint32_t>(epoch), 0x80000000u), key);
         const uint32_t bits[4] = {r.x, r.y, r.z, r.w};
         for (int g = 0; g < a.G && g < 4; ++g) a.goal[g * a.n + w] = static_cast<int32_t>(bits[g] % static_cast<uint32_t>(a.goal_mod[g]));
     }
 }
+
+__global__ void bump_epoch_kernel(unsigned long long *epoch) { *epoch += 1ull; }
 
 // ---- program table -----------------------------------------------------------------------------
 typedef void (*KernelFn)(StepArgs);
@@ -1019,8 +1023,8 @@ extern "C" int mpe_step_host(mpe_handle h, void *pv, const void *lm, float *comm
     return rc;
 }
 
-extern "C" int mpe_reset(mpe_handle h, void *pv, void *lm, float *comm, int32_t *goal, const uint8_t *mask,
-                         uint64_t seed, uint64_t world_offset, uint64_t epoch, void *stream) {
+static int reset_impl(mpe_handle h, void *pv, void *lm, float *comm, int32_t *goal, const uint8_t *mask,
+                      uint64_t seed, uint64_t world_offset, uint64_t epoch, unsigned long long *epoch_dev, void *stream) {
     if (!h) return MPE_ERR_BAD_ARG;
     if (h->device < 0) return MPE_ERR_NO_DEVICE;
     StepArgs tmp{};
@@ -1030,7 +1034,7 @@ extern "C" int mpe_reset(mpe_handle h, void *pv, void *lm, float *comm, int32_t 
     ResetArgs a{};
     a.n = h->n; a.A = p->A; a.L = p->L; a.NC = p->NS * p->DIMC; a.G = p->G;
     a.pv = static_cast<float4 *>(pv); a.lm = static_cast<float2 *>(lm); a.comm = comm; a.goal = goal; a.mask = mask;
-    a.seed = seed; a.world_offset = world_offset; a.epoch = epoch;
+    a.seed = seed; a.world_offset = world_offset; a.epoch = epoch; a.epoch_dev = epoch_dev;
     a.agent_range = 1.0f;  // every scenario: agents ~ U(-1, +1)^2
     // landmarks: U(-1,+1) (simple.py:37, simple_spread.py:44) or U(-0.9,+0.9) (simple_tag.py:53, simple_world_comm.py:105-113)
     const bool narrow = (p->scenario == MPE_SCN_TAG || p->scenario == MPE_SCN_WORLD_COMM);
@@ -1042,10 +1046,26 @@ extern "C" int mpe_reset(mpe_handle h, void *pv, void *lm, float *comm, int32_t 
     const unsigned blocks = static_cast<unsigned>((h->n + 255) / 256);
     reset_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
     cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && epoch_dev) {
+        bump_epoch_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(epoch_dev);
+        e = cudaGetLastError();
+        __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED);
+    }
     if (prev != h->device) cudaSetDevice(prev);
     if (e != cudaSuccess) return cuda_fail(e, "reset_kernel");
     __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED);
     return MPE_OK;
+}
+
+extern "C" int mpe_reset(mpe_handle h, void *pv, void *lm, float *comm, int32_t *goal, const uint8_t *mask,
+                         uint64_t seed, uint64_t world_offset, uint64_t epoch, void *stream) {
+    return reset_impl(h, pv, lm, comm, goal, mask, seed, world_offset, epoch, nullptr, stream);
+}
+
+extern "C" int mpe_reset_dev_epoch(mpe_handle h, void *pv, void *lm, float *comm, int32_t *goal, const uint8_t *mask,
+                                   uint64_t seed, uint64_t world_offset, unsigned long long *epoch_dev, void *stream) {
+    if (!epoch_dev) return MPE_ERR_BAD_ARG;
+    return reset_impl(h, pv, lm, comm, goal, mask, seed, world_offset, 0, epoch_dev, stream);
 }
 
 extern "C" const char *mpe_strerror(int err) {

@@ -157,6 +157,7 @@ class NativeWorld(ShapeHandle):
         self.seed = int(seed)
         self.world_offset = int(world_offset)
         self.epoch = 0
+        self._epoch_dev = None
         # layout of FreshOutputs' float slab, in 4-byte words (every part 64-word = 256-byte aligned)
         off, obs_l = 0, []
         for od in self.obs_dims:
@@ -194,9 +195,27 @@ class NativeWorld(ShapeHandle):
                 raise ValueError("reset mask must have one entry per world")
             mptr = mask.data_ptr()
         pv, lm, comm, goal = self._state_ptrs()
+        if self.torch.cuda.is_current_stream_capturing():
+            # inside a CUDA-graph capture the epoch must live on the device, or every replay would redraw the
+            # same initial conditions
+            if self._epoch_dev is None:
+                raise RuntimeError("call NativeWorld.enable_device_epoch() before capturing a reset in a CUDA graph")
+            check(self.lib.mpe_reset_dev_epoch(self.handle, pv, lm, comm, goal, mptr, self.seed, self.world_offset,
+                                               self._epoch_dev.data_ptr(), self._stream()), "mpe_reset_dev_epoch")
+            return
+        if self._epoch_dev is not None:
+            self.epoch = int(self._epoch_dev.item())
         check(self.lib.mpe_reset(self.handle, pv, lm, comm, goal, mptr, self.seed, self.world_offset,
                                  self.epoch, self._stream()), "mpe_reset")
         self.epoch += 1
+        if self._epoch_dev is not None:
+            self._epoch_dev.fill_(self.epoch)
+
+    def enable_device_epoch(self):
+        """keep the reset epoch in device memory so that resets captured in CUDA graphs advance it on replay"""
+        if self._epoch_dev is None:
+            self._epoch_dev = self.torch.full((1,), self.epoch, dtype=self.torch.int64, device=self.device)
+        return self._epoch_dev
 
     # ---- the hot path ------------------------------------------------------------------------
     def set_action(self, act_ptrs, flags=0):

@@ -10,14 +10,16 @@ persistent output slab (`env.reuse_buffers`), so nothing is allocated while the 
 
 
 class GraphedRollout(object):
-    def __init__(self, env, policy, steps, warmup=2):
+    def __init__(self, env, policy, steps, warmup=2, reset_every=None):
         import torch
         if not env.world.batched:
             raise ValueError("GraphedRollout needs a batched env (make_env(..., num_envs=N))")
         self.env, self.policy, self.steps = env, policy, int(steps)
+        self.reset_every = reset_every        # e.g. 25: env.reset() inside the graph every 25 steps (fresh draws per replay)
         self.torch = torch
         env.reuse_buffers = True
         nw = env.world.bind()
+        nw.enable_device_epoch()
         self.obs = [o.clone() for o in env.reset()]          # static input buffers of the graph
         self.rew_sum = torch.zeros(env.n, nw.n_env, device=nw.device)
         self.stream = torch.cuda.Stream(nw.device)
@@ -33,11 +35,13 @@ class GraphedRollout(object):
         torch = self.torch
         obs = self.obs
         self.rew_sum.zero_()
-        for _ in range(self.steps):
+        for t in range(self.steps):
             with torch.no_grad():
                 act = self.policy(obs)
             obs, rew_n, done_n, _ = self.env.step([a.contiguous() for a in act])
             self.rew_sum += torch.stack(list(rew_n))
+            if self.reset_every and (t + 1) % self.reset_every == 0:
+                obs = self.env.reset()
         for dst, src in zip(self.obs, obs):                  # the next replay continues from here
             dst.copy_(src)
 

@@ -187,3 +187,23 @@ def test_graphed_rollout_matches_eager():
     for a, b in zip(obs_g, obs):
         assert torch.equal(a, b)
     assert torch.equal(rew_g, tot)
+
+
+def test_graphed_rollout_with_resets_draws_fresh_episodes_on_replay():
+    """a reset captured in the graph reads its epoch from device memory, so each replay starts new episodes"""
+    from multiagent_particle_envs_b200.rollout import GraphedRollout
+    n = 2048
+    env = make_product_env("simple_spread_n3", num_envs=n, seed=5)
+    roll = GraphedRollout(env, lambda obs_n: [torch.softmax(o[:, :5], 1) for o in obs_n], steps=10, reset_every=10)
+    nw = env.world.native
+    roll.run()
+    torch.cuda.synchronize()
+    first = nw.lm_p.clone()
+    e1 = int(nw._epoch_dev.item())
+    roll.run()
+    torch.cuda.synchronize()
+    assert int(nw._epoch_dev.item()) == e1 + 1
+    assert not torch.equal(first, nw.lm_p)                      # new landmark draws after the replayed reset
+    assert float(nw.agent_pv[:, :, 2:4].abs().max()) == 0.0      # ... and the episode really was reset
+    env.reset()                                                  # eager resets keep advancing the same counter
+    assert int(nw._epoch_dev.item()) == e1 + 2
