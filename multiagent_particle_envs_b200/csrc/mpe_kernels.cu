@@ -30,8 +30,9 @@ __device__ __forceinline__ void static_for(F &&f) {
 template <class P>
 struct Shape {
     // warp-private staging, in floats: [mbarrier: 4][action tiles of all agents][observation tiles]
-    // Dense observation tiles (exact images of the global rows) each get their own slot so that all
-    // of them can be in flight as TMA bulk stores at once; padded tiles share one slot.
+    // Dense observation tiles (exact images of the global rows) each get their own slot, so that the
+    // rows of all agents are written first and then streamed out after ONE __syncwarp; padded tiles
+    // share one slot.
     static constexpr int kBarFloats = 4;
     __host__ __device__ static constexpr int act_floats(int i) { return 32 * (P::act_dim(i) | 1); }
     __host__ __device__ static constexpr int act_off(int i) { int s = kBarFloats; for (int j = 0; j < i; ++j) s += act_floats(j); return s; }
@@ -135,7 +136,8 @@ __global__ void __launch_bounds__(kMaxThreads, MPE_MIN_BLOCKS) mpe_kernel(const 
     uint64_t *bar = reinterpret_cast<uint64_t *>(s_warp);
     const DevDesc &d = a.d;
 
-    // ---- action tiles: TMA bulk loads issued FIRST, so that they fly together with the state loads --
+    // ---- action tiles: asynchronous copies (cp.async, or TMA bulk) issued FIRST, so that they fly together
+    //      with the state loads -------------------------------------------------------------------------
     bool bulk = false;
     if constexpr ((MODE == kFusedStep || MODE == kSetAction) && Shape<P>::all_act_dense()) {
         uintptr_t bits = 0;
@@ -822,7 +824,7 @@ static int fill_outputs(mpe_handle h, StepArgs &a, float *const *obs_n, float *r
     const Program *p = h->prog;
     if (!obs_n || !ok4(rew) || !done) return MPE_ERR_BAD_ARG;
     for (int i = 0; i < p->A; ++i) {
-        if (!ok16(obs_n[i])) return MPE_ERR_BAD_ARG;   // observation rows are written as 16-byte / TMA bulk stores
+        if (!ok16(obs_n[i])) return MPE_ERR_BAD_ARG;   // observation rows are written as 16-byte stores
         a.obs[i] = obs_n[i];
     }
     a.rew = rew;
