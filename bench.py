@@ -30,6 +30,9 @@ import sys
 import threading
 import time
 
+# NCCL announces its version on stdout at init (NCCL_DEBUG=VERSION / WARN); rank 0 must print exactly one line on
+# stdout, so NCCL's log goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 # the CPU arms run one world per process: keep NumPy / torch thread pools from oversubscribing the host
 for _v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
     os.environ.setdefault(_v, "1")
