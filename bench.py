@@ -30,9 +30,6 @@ import sys
 import threading
 import time
 
-# NCCL announces its version on stdout at init (NCCL_DEBUG=VERSION / WARN); rank 0 must print exactly one line on
-# stdout, so NCCL's log goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 # the CPU arms run one world per process: keep NumPy / torch thread pools from oversubscribing the host
 for _v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
     os.environ.setdefault(_v, "1")
@@ -259,7 +256,19 @@ def run_b200_arm(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints a "NCCL version ..." banner on stdout when its communicator is created; rank 0 must print
+        # exactly ONE line on stdout, so file descriptor 1 points at stderr while the communicator comes up
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     lib = _lib.load()
 
     # ---- ring of independent batches, each with resident actions and outputs -------------------
