@@ -506,6 +506,7 @@ struct Program {
     int lanes_smem, lanes_wpw;
     int A, L, NS, DIMC, INFO, G;
     int obs_dim[kMaxA], act_dim[kMaxA];
+    int unread_state_floats;   // state floats per world that this scenario's step never needs (not compulsory traffic)
 };
 
 template <class P>
@@ -520,6 +521,10 @@ static Program make_program() {
     p.smem_bytes = Shape<P>::kWarpBytes;  // per warp
     p.A = P::A; p.L = P::L; p.NS = P::NS; p.DIMC = P::DIMC; p.INFO = P::INFO; p.G = P::G;
     for (int i = 0; i < P::A; ++i) { p.obs_dim[i] = P::obs_dim(i); p.act_dim[i] = P::act_dim(i); }
+    // simple_crypto never looks at a position (nobody moves, observations and rewards are about utterances only);
+    // simple_speaker_listener never looks at the immovable speaker's position
+    p.unread_state_floats = P::kScenario == MPE_SCN_CRYPTO ? 4 * P::A + 2 * P::L
+                          : (P::kScenario == MPE_SCN_SPEAKER_LISTENER ? 4 : 0);
     return p;
 }
 
@@ -723,7 +728,7 @@ extern "C" int64_t mpe_bytes_per_env_step(mpe_handle h) {
     // read agent pos+vel, landmark pos, goal indices, actions; write pos+vel of the movable
     // agents, observations, rewards, speaker comm state, 1 done byte per agent
     const Program *p = h->prog;
-    int64_t f = 4 * p->A + 2 * p->L + p->G + p->A + p->NS * p->DIMC;
+    int64_t f = 4 * p->A + 2 * p->L + p->G + p->A + p->NS * p->DIMC - p->unread_state_floats;
     for (int i = 0; i < p->A; ++i) f += p->act_dim[i] + p->obs_dim[i] + (h->desc.agent_movable[i] ? 4 : 0);
     return 4 * f + p->A;
 }

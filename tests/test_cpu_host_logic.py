@@ -57,8 +57,9 @@ def test_shapes_spaces_and_descriptor(tag):
     assert sh.act_dims == act == [int(d) for d in g["prop_act_dims"]]
     A, L, C = n, len(g["prop_landmark_size"]), int(g["prop_dim_c"])
     mov, sil = list(g["prop_agent_movable"]), list(g["prop_agent_silent"])
+    unread = {"simple_crypto": 4 * A + 2 * L, "simple_speaker_listener": 4}.get(tag, 0)   # positions nobody needs
     formula = 4 * (4 * A + 2 * L + N_GOALS.get(tag, 0) + sum(act) + 4 * sum(mov) + sum(obs) + A
-                   + C * sum(1 - x for x in sil)) + A        # SURVEY.md 8(d), compulsory traffic
+                   + C * sum(1 - x for x in sil) - unread) + A        # SURVEY.md 8(d), compulsory traffic
     assert sh.bytes_per_env_step == formula and (nbytes is None or nbytes == formula)
     assert sh.n_goals == N_GOALS.get(tag, 0)
     for i, sp in enumerate(env.action_space):
