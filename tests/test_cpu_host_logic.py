@@ -244,3 +244,26 @@ def test_custom_scenario_descriptor_and_shape_only_handle():
     world.agents.append(Agent())
     with pytest.raises(ValueError):          # more than 8 agents
         world.descriptor()
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver launches) prints exactly one JSON line with the contract's keys"""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1",
+                          "--steps", "60", "--warmup", "5"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    r = json.loads(lines[0])
+    assert r["impl"] == "reference" and r["metric"] == "env_steps_per_sec" and r["unit"] == "env-steps/s"
+    assert r["n_gpus"] == 1 and r["steps"] == 60 and r["warmup"] == 5 and r["higher_is_better"] is True
+    assert r["value"] > 100 and r["vs_baseline"] is None and r["data"] == "synthetic" and r["dtype"] == "f64"
+    cb = r["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == r["value"] and "np_port" in cb["sample"]
+    assert r["e2e"] == {"value": r["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert r["config"]["workload"].startswith("simple_spread N=3") and r["config"]["n_env_per_gpu"] == 65536
+    # under torchrun every rank but 0 exits silently
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+                          "--steps", "10", "--warmup", "3"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
