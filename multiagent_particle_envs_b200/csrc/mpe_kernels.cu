@@ -713,7 +713,7 @@ extern "C" int mpe_destroy(mpe_handle h) {
 }
 
 extern "C" int mpe_num_agents(mpe_handle h) { return h ? h->prog->A : MPE_ERR_BAD_ARG; }
-extern "C" int64_t mpe_num_envs(mpe_handle h) { return h ? h->n : MPE_ERR_BAD_ARG; }
+extern "C" int64_t mpe_num_envs(mpe_handle h) { return h ? h->n : static_cast<int64_t>(MPE_ERR_BAD_ARG); }
 extern "C" int mpe_obs_dim(mpe_handle h, int i) {
     if (!h || i < 0 || i >= h->prog->A) return MPE_ERR_BAD_ARG;
     return h->prog->scenario == MPE_SCN_CUSTOM ? MPE_ERR_UNSUPPORTED : h->prog->obs_dim[i];
