@@ -114,8 +114,9 @@ class ClockSampler(object):
 # ------------------------------------------------------------------------------------------------
 # CPU arm.  Two ports of the reference path live under oracle/ (test + baseline infrastructure):
 #   np_port.py     per-world NumPy float64, the reference's own granularity (one world per process) --
-#                  the stand-in for "the reference's own NumPy path" (measured within 2 % of the real
-#                  reference in the build container: 26.0k vs 26.4k env-steps/s on 8 cores)
+#                  the stand-in for "the reference's own NumPy path"; measured next to the real reference in the
+#                  build container it is 1.1-1.5x FASTER than it (tools/compare_reference_speed.py,
+#                  profiles/r1_cpu_reference_vs_port.json), i.e. a conservative baseline
 #   mpe_oracle.c   the C checker; ~300x faster than the reference itself; reported alongside
 # ------------------------------------------------------------------------------------------------
 def _spread_desc():
