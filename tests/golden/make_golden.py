@@ -98,7 +98,7 @@ def flatten_info(name, info_n):
     return np.array([r + [0.0] * (width - len(r)) for r in out], dtype=np.float64)   # ragged rows zero-padded
 
 
-def run_config(name, n, W, T, seed, force_discrete=False):
+def run_config(name, n, W, T, seed, force_discrete=False, discrete_input=False):
     rng = np.random.RandomState(seed)
     rec = dict(pv0=[], lm=[], comm0=[], goal=[], act=[], pv=[], comm=[], obs=[], rew=[], done=[], info=[])
     props = None
@@ -106,6 +106,7 @@ def run_config(name, n, W, T, seed, force_discrete=False):
         np.random.seed(seed * 1000 + w)
         env = refshim.make_reference_env(name, n)
         env.force_discrete_action = force_discrete
+        env.discrete_action_input = discrete_input      # integer actions (environment.py:161-167)
         env.reset()
         world = env.world
         if props is None:
@@ -136,6 +137,9 @@ def run_config(name, n, W, T, seed, force_discrete=False):
             acts = []
             for i, sp in enumerate(env.action_space):
                 d = act_dim(sp)
+                if discrete_input:
+                    acts.append(np.array([float(rng.randint(0, d))]))
+                    continue
                 if not world.agents[i].movable:          # speaker-only agents: the comm chunk
                     a = rng.uniform(0, 1, d) * (rng.uniform() > 0.15)   # sometimes an all-zero utterance
                 else:
@@ -144,7 +148,7 @@ def run_config(name, n, W, T, seed, force_discrete=False):
                     p = np.exp(logits - logits.max())
                     a = np.concatenate([p / p.sum(), rng.uniform(0, 1, d - 5)]) if d > 5 else p / p.sum()
                 acts.append(a)
-            obs_n, rew_n, done_n, info_n = env.step([a.copy() for a in acts])
+            obs_n, rew_n, done_n, info_n = env.step([int(a[0]) for a in acts] if discrete_input else [a.copy() for a in acts])
             pv, comm = snapshot(world)
             steps["act"].append(np.concatenate(acts))
             steps["pv"].append(pv)
@@ -159,6 +163,7 @@ def run_config(name, n, W, T, seed, force_discrete=False):
     for k, v in props.items():
         out["prop_" + k] = np.array(v)
     out["force_discrete"] = np.array(int(force_discrete))
+    out["discrete_input"] = np.array(int(discrete_input))
     return out
 
 
@@ -179,7 +184,7 @@ def kat():
             a[2 if name == "simple" else min(i + 1, 4)] = 1.0
             acts.append(a)
         for _ in range(2):
-            obs_n, rew_n, done_n, info_n = env.step([a.copy() for a in acts])
+            obs_n, rew_n, done_n, info_n = env.step([int(a[0]) for a in acts] if discrete_input else [a.copy() for a in acts])
         pv, comm = snapshot(env.world)
         out[name + "/pv0"], out[name + "/lm"], out[name + "/comm0"] = pv0, lm, comm0
         out[name + "/act"] = np.concatenate(acts)
@@ -203,6 +208,8 @@ def main():
         return
     data = run_config("simple_tag", None, 8, 10, seed=77, force_discrete=True)
     np.savez_compressed(os.path.join(HERE, "simple_tag_force_discrete.npz"), **data)
+    data = run_config("simple_tag", None, 8, 10, seed=78, discrete_input=True)
+    np.savez_compressed(os.path.join(HERE, "simple_tag_discrete_input.npz"), **data)
     np.savez_compressed(os.path.join(HERE, "kat.npz"), **kat())
 
 

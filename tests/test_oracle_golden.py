@@ -18,13 +18,13 @@ def goal_of(g):
     return g["goal"] if "goal" in g and g["goal"].shape[1] > 0 else None
 
 
-@pytest.mark.parametrize("tag", TAGS + ["simple_tag_force_discrete"])
+@pytest.mark.parametrize("tag", TAGS + ["simple_tag_force_discrete", "simple_tag_discrete_input"])
 def test_oracle_f64_trajectory_matches_reference(tag):
     g = load_golden(tag)
     base = "simple_tag" if tag.startswith("simple_tag") else tag
     orc = Oracle(descriptor(base), "f64")
     assert orc.obs_dims == list(g["prop_obs_dims"]) and orc.act_dims == list(g["prop_act_dims"])
-    flags = step_flags(g)
+    flags = step_flags(g) | (4 if int(g.get("discrete_input", 0)) else 0)      # MPE_FLAG_DISCRETE_ACTION_INPUT
     pv, comm, lm = g["pv0"], g["comm0"], g["lm"]
     W, T = g["act"].shape[:2]
     for t in range(T):
