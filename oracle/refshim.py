@@ -134,5 +134,34 @@ def make_reference_env(name, n=None):
         scenario.reset_world(world)
         return MultiAgentEnv(world, scenario.reset_world, scenario.reward, scenario.observation,
                              scenario.benchmark_data)
+    if name == "simple_tag" and isinstance(n, tuple):
+        # (num_adversaries, num_good_agents, num_landmarks) other than the hard-coded 3/1/2: the world is built
+        # test-side with the reference's own property assignments (simple_tag.py:16-33); its reset_world / reward /
+        # observation / benchmark_data are generic over world.agents / world.landmarks and are reused unchanged
+        from multiagent.core import World, Agent, Landmark
+        from multiagent.environment import MultiAgentEnv
+        import multiagent.scenarios as scenarios
+        scenario = scenarios.load("simple_tag.py").Scenario()
+        n_adv, n_good, n_lm = n
+        world = World()
+        world.dim_c = 2
+        world.agents = [Agent() for _ in range(n_adv + n_good)]
+        for i, agent in enumerate(world.agents):
+            agent.name = "agent %d" % i
+            agent.collide = True
+            agent.silent = True
+            agent.adversary = i < n_adv
+            agent.size = 0.075 if agent.adversary else 0.05
+            agent.accel = 3.0 if agent.adversary else 4.0
+            agent.max_speed = 1.0 if agent.adversary else 1.3
+        world.landmarks = [Landmark() for _ in range(n_lm)]
+        for i, landmark in enumerate(world.landmarks):
+            landmark.name = "landmark %d" % i
+            landmark.collide = True
+            landmark.movable = False
+            landmark.size = 0.2
+            landmark.boundary = False
+        scenario.reset_world(world)
+        return MultiAgentEnv(world, scenario.reset_world, scenario.reward, scenario.observation, scenario.benchmark_data)
     return make_env(name, benchmark=(name not in ("simple", "simple_push", "simple_reference",
                                                   "simple_speaker_listener")))

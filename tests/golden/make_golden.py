@@ -210,6 +210,9 @@ def main():
     np.savez_compressed(os.path.join(HERE, "simple_tag_force_discrete.npz"), **data)
     data = run_config("simple_tag", None, 8, 10, seed=78, discrete_input=True)
     np.savez_compressed(os.path.join(HERE, "simple_tag_discrete_input.npz"), **data)
+    for counts, tag in (((1, 1, 2), "simple_tag_1v1"), ((4, 2, 2), "simple_tag_4v2"), ((6, 2, 3), "simple_tag_6v2")):
+        data = run_config("simple_tag", counts, 6, 10, seed=80 + counts[0])     # entity-count variants
+        np.savez_compressed(os.path.join(HERE, tag + ".npz"), **data)
     np.savez_compressed(os.path.join(HERE, "kat.npz"), **kat())
 
 

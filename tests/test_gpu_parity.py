@@ -6,7 +6,8 @@ on the kernels' own stored state.  Run on the B200 box: pytest -m gpu."""
 import numpy as np
 import pytest
 
-from helpers import CONFIGS, load_golden, make_product_env, random_actions, random_goals, random_states, split_cols
+from helpers import (CONFIGS, VARIANTS, load_golden, make_product_env, random_actions, random_goals, random_states,
+                     split_cols)
 
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
@@ -56,11 +57,14 @@ def gpu_step(env, act, flags_expected=None):
     return obs, rew, done, info
 
 
-@pytest.mark.parametrize("tag", TAGS + ["simple_tag_force_discrete"])
+GOLDEN_VARIANTS = ["simple_tag_1v1", "simple_tag_4v2", "simple_tag_6v2"]   # reference worlds with other entity counts
+
+
+@pytest.mark.parametrize("tag", TAGS + ["simple_tag_force_discrete"] + GOLDEN_VARIANTS)
 def test_golden_fixtures_single_step(tag):
     """every recorded reference step, state re-injected each step"""
     g = load_golden(tag)
-    base = "simple_tag" if tag.startswith("simple_tag") else tag
+    base = tag if tag in VARIANTS else ("simple_tag" if tag.startswith("simple_tag") else tag)
     W, T = g["act"].shape[:2]
     env = make_product_env(base, num_envs=W)
     env.force_discrete_action = bool(int(g["force_discrete"]))

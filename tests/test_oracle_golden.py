@@ -18,10 +18,14 @@ def goal_of(g):
     return g["goal"] if "goal" in g and g["goal"].shape[1] > 0 else None
 
 
-@pytest.mark.parametrize("tag", TAGS + ["simple_tag_force_discrete", "simple_tag_discrete_input"])
+VARIANT_TAGS = ["simple_tag_1v1", "simple_tag_4v2", "simple_tag_6v2"]   # worlds the reference's callbacks support but its
+#                                                                           make_world hard-codes away (built test-side)
+
+
+@pytest.mark.parametrize("tag", TAGS + ["simple_tag_force_discrete", "simple_tag_discrete_input"] + VARIANT_TAGS)
 def test_oracle_f64_trajectory_matches_reference(tag):
     g = load_golden(tag)
-    base = "simple_tag" if tag.startswith("simple_tag") else tag
+    base = tag if tag in VARIANT_TAGS else ("simple_tag" if tag.startswith("simple_tag") else tag)
     orc = Oracle(descriptor(base), "f64")
     assert orc.obs_dims == list(g["prop_obs_dims"]) and orc.act_dims == list(g["prop_act_dims"])
     flags = step_flags(g) | (4 if int(g.get("discrete_input", 0)) else 0)      # MPE_FLAG_DISCRETE_ACTION_INPUT
