@@ -80,10 +80,11 @@ def test_golden_fixtures_single_step(tag):
         np.testing.assert_allclose(obs, g["obs"][:, t], rtol=RTOL, atol=ATOL)
         assert np.array_equal(done, g["done"][:, t])
         ok = np.isclose(rew, g["rew"][:, t], rtol=RTOL, atol=5e-6)
-        assert ok.mean() >= 0.99, (t, ok.mean())   # a flipped contact flag changes a reward by >= 1
+        # a contact flag evaluated in fp32 may differ from fp64 within 1e-7 of the threshold; it changes a reward by >= 1
+        assert (~ok).sum() <= max(1, ok.size // 100), (t, ok.mean())
         if info.shape[2]:
             okc = np.isclose(info, g["info"][:, t], rtol=RTOL, atol=5e-6)
-            assert okc.mean() >= 0.99
+            assert (~okc).sum() <= max(1, okc.size // 100)
 
 
 @pytest.mark.parametrize("tag", TAGS)
