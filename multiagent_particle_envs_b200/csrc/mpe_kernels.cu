@@ -124,9 +124,9 @@ __global__ void __launch_bounds__(kMaxThreads, MPE_MIN_BLOCKS) mpe_kernel(const 
     const int64_t n = a.n;
     const int64_t end = a.begin + a.count;
     const int64_t w0 = a.begin + (static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + warp) * 32;
-    // Programmatic dependent launch (opt-in, MPE_B200_PDL=1|2): the index arithmetic and the first touches of the
+    // Programmatic dependent launch (MPE_B200_PDL, see launch()): the index arithmetic and the first touches of the
     // parameter block (constant-bank misses) run before the wait; no global memory is touched before the previous
-    // grid has completed and flushed.
+    // grid has completed and flushed.  A warp that exits early counts as having released the dependent grid.
     if (a.flags & kFlagPdlEarly) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (w0 >= end) return;  // whole warp exits together
     const int rows = (end - w0) < 32 ? static_cast<int>(end - w0) : 32;
