@@ -161,9 +161,9 @@ def cpu_numpy_port(budget_s, steps=None, warmup=100, max_seconds=None):
         pass
     return {"value": total, "unit": UNIT, "cores": procs, "kind": "port", "cpu_model": cpu_model,
             "sample": "%d processes (best of the probed counts; affinity reports %d CPUs) x %d env.step calls of one "
-                      "simple_spread world each (oracle/np_port.py: per-world NumPy float64 restatement at the reference's "
+                      "%s world each (oracle/np_port.py: per-world NumPy float64 restatement at the reference's "
                       "granularity, softmax actions, reset every 25 steps); %.1f s wall"
-                      % (procs, len(os.sched_getaffinity(0)), steps, dt),
+                      % (procs, len(os.sched_getaffinity(0)), steps, SCENARIO, dt),
             "per_process": total / procs, "steps_per_process": steps, "seconds": dt}
 
 
@@ -438,7 +438,7 @@ def run_b200_arm(args, rank, local_rank, world):
             except Exception:  # noqa: BLE001
                 traffic = None
         cpu = None
-        if world == 1 and args.cpu_seconds > 0 and SCENARIO in ("simple", "simple_spread", "simple_tag", "simple_world_comm"):
+        if world == 1 and args.cpu_seconds > 0:
             cpu = cpu_baseline_block(args.cpu_seconds, 5.0 if SCENARIO == "simple_spread" and not SCENARIO_KW else 0.0)[0]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

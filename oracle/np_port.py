@@ -32,6 +32,12 @@ class WorldSpec(object):
         self.adversary = [bool(d.agent_adversary[i]) for i in range(A)]
         self.leader = [bool(d.agent_leader[i]) for i in range(A)]
         self.n_obstacles, self.n_food = int(d.n_obstacles), int(d.n_food)
+        # landmark colours the observation functions embed (simple_push.py:34-37, simple_speaker_listener.py:44-46,
+        # simple_reference.py:37-39, simple_crypto.py:58-62)
+        self.push_lm_color = [np.array([0.1 + (0.8 if c == l + 1 else 0.0) for c in range(3)]) for l in range(L)]
+        self.sl_lm_color = [np.array([0.65 if c == l else 0.15 for c in range(3)]) for l in range(L)]
+        self.ref_lm_color = [np.array([0.75 if c == l else 0.25 for c in range(3)]) for l in range(L)]
+        self.crypto_color = [np.eye(max(self.C, 1))[l] for l in range(L)] if self.C >= L else []
 
 
 def decode_actions(spec, action_n, force_discrete=False):
@@ -108,8 +114,10 @@ def _bound(x):                                                   # simple_tag.py
     return min(np.exp(2 * x - 2), 10)
 
 
-def observe(spec, pos, vel, comm, shared_reward=False):
-    """scenario.observation / reward for every agent + the step glue (environment.py:92-102)"""
+def observe(spec, pos, vel, comm, shared_reward=False, goal=None):
+    """scenario.observation / reward for every agent + the step glue (environment.py:92-102); `goal` holds the
+    per-world goal indices reset_world draws with np.random.choice (adversary, push, speaker_listener: [g];
+    reference: [goal_b of agent 0, goal_b of agent 1]; crypto: [goal, key])"""
     A, L = spec.A, spec.L
     lm = pos[A:]
     obs, rew = [], []
@@ -197,6 +205,69 @@ def observe(spec, pos, vel, comm, shared_reward=False):
                 obs.append(np.concatenate([vel[i], pos[i]] + ent + other_pos + other_vel + in_forest + [comm[leader]]))
             else:
                 obs.append(np.concatenate([vel[i], pos[i]] + ent + other_pos + in_forest + other_vel))
+    elif spec.scenario == 4:                                     # simple_adversary.py:76-139
+        g = lm[goal[0]]
+        adv = [i for i in range(A) if spec.adversary[i]]
+        good = [i for i in range(A) if not spec.adversary[i]]
+        for i in range(A):
+            if spec.adversary[i]:
+                rew.append(-np.sum(np.square(pos[i] - g)))                                   # :107-118
+            else:
+                adv_rew = sum(_dist(pos[a], g) for a in adv)                                 # :83
+                pos_rew = -min(_dist(pos[a], g) for a in good)                               # :93-94
+                rew.append(pos_rew + adv_rew)
+            ent = [lm[l] - pos[i] for l in range(L)]
+            other = [pos[j] - pos[i] for j in range(A) if j != i]
+            obs.append(np.concatenate(ent + other) if spec.adversary[i] else np.concatenate([g - pos[i]] + ent + other))
+    elif spec.scenario == 5:                                     # simple_push.py:58-96
+        g = lm[goal[0]]
+        good = [i for i in range(A) if not spec.adversary[i]]
+        for i in range(A):
+            if spec.adversary[i]:
+                rew.append(min(_dist(pos[a], g) for a in good) - _dist(g, pos[i]))           # :66-74
+            else:
+                rew.append(-_dist(pos[i], g))                                                # :62-64
+            ent = [lm[l] - pos[i] for l in range(L)]
+            other = [pos[j] - pos[i] for j in range(A) if j != i]
+            if spec.adversary[i]:
+                obs.append(np.concatenate([vel[i]] + ent + other))
+            else:
+                color = np.array([0.25, 0.25, 0.25])
+                color[goal[0] + 1] += 0.5                                                    # :47-53
+                obs.append(np.concatenate([vel[i], g - pos[i], color] + ent + spec.push_lm_color + other))
+    elif spec.scenario == 6:                                     # simple_speaker_listener.py:63-92
+        r = -np.sum(np.square(pos[1] - lm[goal[0]]))
+        rew = [r, r]
+        obs.append(np.concatenate([spec.sl_lm_color[goal[0]]]))                              # speaker :87-88
+        obs.append(np.concatenate([vel[1]] + [lm[l] - pos[1] for l in range(L)] + [comm[0]]))   # listener :90-92
+    elif spec.scenario == 7:                                     # simple_reference.py:55-80
+        for i in range(A):
+            o = 1 - i
+            rew.append(-np.sum(np.square(pos[o] - lm[goal[i]])))
+            obs.append(np.concatenate([vel[i]] + [lm[l] - pos[i] for l in range(L)] + [spec.ref_lm_color[goal[i]], comm[o]]))
+    elif spec.scenario == 8:                                     # simple_crypto.py:94-174
+        gcol, key = spec.crypto_color[goal[0]], spec.crypto_color[goal[1]]
+        zero = np.zeros(spec.C)
+        for i in range(A):
+            if spec.adversary[i]:                                                            # :115-121
+                r = 0
+                if not (comm[i] == zero).all():
+                    r -= np.sum(np.square(comm[i] - gcol))
+            else:                                                                            # :94-113
+                good_rew, adv_rew = 0, 0
+                for a in range(A):
+                    if not spec.adversary[a] and a != 2 and not (comm[a] == zero).all():
+                        good_rew -= np.sum(np.square(comm[a] - gcol))
+                    if spec.adversary[a] and not (comm[a] == zero).all():
+                        adv_rew += np.sum(np.square(comm[a] - gcol))
+                r = adv_rew + good_rew
+            rew.append(r)
+            if i == 2:
+                obs.append(np.concatenate([gcol, key]))
+            elif not spec.adversary[i]:
+                obs.append(np.concatenate([key, comm[2]]))
+            else:
+                obs.append(np.concatenate([comm[2]]))
     else:
         raise NotImplementedError("scenario %d" % spec.scenario)
     done = [False] * A                                           # environment.py:132-135
@@ -205,11 +276,11 @@ def observe(spec, pos, vel, comm, shared_reward=False):
     return obs, rew, done
 
 
-def env_step(spec, pos, vel, comm, action_n, shared_reward=False, force_discrete=False):
+def env_step(spec, pos, vel, comm, action_n, shared_reward=False, force_discrete=False, goal=None):
     """MultiAgentEnv.step (environment.py:80-104) for one world"""
     u, c = decode_actions(spec, action_n, force_discrete)
     world_step(spec, pos, vel, comm, u, c)
-    return observe(spec, pos, vel, comm, shared_reward)
+    return observe(spec, pos, vel, comm, shared_reward, goal)
 
 
 # ---- timing helper used by bench.py ---------------------------------------------------------------
@@ -230,23 +301,27 @@ def _worker(args):
     vel = np.zeros((spec.A, 2))
     comm = np.zeros((spec.A, spec.C))
     adims = [(5 if spec.movable[i] else 0) + (0 if spec.silent[i] else spec.C) for i in range(spec.A)]
+    goal = [int(rng.randint(0, max(spec.L, 1))), int(rng.randint(0, max(spec.L, 1)))]
 
     def acts():
         out = []
-        for dmn in adims:
-            z = rng.randn(5)
-            e = np.exp(z - z.max())
-            out.append(np.concatenate([e / e.sum(), rng.uniform(0, 1, dmn - 5)]))
+        for i, dmn in enumerate(adims):
+            if spec.movable[i]:
+                z = rng.randn(5)
+                e = np.exp(z - z.max())
+                out.append(np.concatenate([e / e.sum(), rng.uniform(0, 1, dmn - 5)]))
+            else:
+                out.append(rng.uniform(0, 1, dmn))
         return out
 
     for t in range(warmup):
-        env_step(spec, pos, vel, comm, acts(), shared)
+        env_step(spec, pos, vel, comm, acts(), shared, goal=goal)
     t0 = time.perf_counter()
     for t in range(steps):
         if t % 25 == 0:
             pos[:spec.A] = rng.uniform(-1, 1, (spec.A, 2))
             vel[:] = 0
-        env_step(spec, pos, vel, comm, acts(), shared)
+        env_step(spec, pos, vel, comm, acts(), shared, goal=goal)
     return steps / (time.perf_counter() - t0)
 
 

@@ -11,7 +11,7 @@ from helpers import CONFIGS, descriptor, load_golden, step_flags
 from oracle import Oracle
 
 TAGS = list(CONFIGS)
-NP_PORT_TAGS = ["simple", "simple_spread_n3", "simple_spread_n6", "simple_tag", "simple_world_comm"]
+NP_PORT_TAGS = list(CONFIGS)
 
 
 def goal_of(g):
@@ -105,7 +105,8 @@ def test_numpy_port_matches_reference(tag):
             for dmn in adims:
                 acts.append(g["act"][w, t, c0:c0 + dmn])
                 c0 += dmn
-            obs, rew, done = np_port.env_step(spec, pos, vel, comm, acts, shared)
+            goal = [int(x) for x in g["goal"][w]] if "goal" in g and g["goal"].shape[1] else None
+            obs, rew, done = np_port.env_step(spec, pos, vel, comm, acts, shared, goal=goal)
             np.testing.assert_allclose(np.concatenate(obs), g["obs"][w, t], rtol=1e-11, atol=1e-13)
             np.testing.assert_allclose(np.array(rew, dtype=np.float64), g["rew"][w, t], rtol=1e-11, atol=1e-12)
             np.testing.assert_allclose(pos[:spec.A], g["pv"][w, t][:, 0:2], rtol=1e-11, atol=1e-13)
