@@ -1,29 +1,41 @@
 #!/usr/bin/env python
 """bench.py -- env-steps/sec of the multiagent-particle-envs hot path on B200.
 
-    python bench.py --gpus N --steps K --warmup W              # this repo (sm_100a kernels)
-    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU arm: the reference path's NumPy port
+    python bench.py --gpus N --steps K --warmup W                    # this repo (sm_100a kernels)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU arm: the reference path on the host cores
 
 A "step" is one pass of the hot path (MultiAgentEnv.step: action decode -> World.step -> observation /
 reward / done, environment.py:80-104) over ONE batch of `n_env` worlds = one fused-kernel launch.
 Workload (BASELINE.json configs[1]): simple_spread N=3, 65 536 worlds per GPU.  Under torchrun every
-rank steps its own 65 536-world shard (weak scaling, no data-path collective); the only exchange is one
-all-gather of the (env_steps, seconds) counters.
+rank steps its own shard (weak scaling, no data-path collective); the only exchange is one all-gather of
+the (env_steps, seconds) counters.  Other BASELINE configs: --scenario / --num-envs / --num-agents.
 
-Timing hygiene: the timed steps rotate over a ring of R independent batches whose combined working set
-is > 2x the 126 MB L2 ("inputs larger than L2"); W >= 3 warm-up steps; CUDA events on the launching
-stream with a barrier + synchronize on both sides; max over ranks; nvidia-smi clocks sampled during the
-timed region.  Episodes are reset every 25 steps of each batch (MADDPG's episode length).
+Timing hygiene
+  * the timed steps rotate over a ring of R independent batches.  R is sized on the INPUT bytes (state +
+    actions, what a step re-reads): R x input bytes > 2 x 126 MB L2, so nothing a step reads can still be
+    L2-resident from its previous visit ("inputs larger than L2"); the outputs are write-only;
+  * EXACTLY the K requested steps are timed, all of them replayed from CUDA graphs captured before the timed
+    region (whole units of R x 25 steps + one graph holding the remainder), whatever K is;
+  * a spin kernel queued in front of the start event keeps the stream busy while the host enqueues the event
+    records and graph launches, so host launch latency is not inside the region even for K = 20;
+  * W >= 3 warm-up steps (+ one untimed replay of every captured graph); CUDA events on the launching
+    stream, barrier + synchronize on both sides, max over ranks; nvidia-smi clocks sampled during the region;
+  * episodes are reset every 25 steps of each batch (MADDPG's episode length), resets inside the region.
 
-value      device-resident throughput: inputs already in HBM, K fused launches replayed from CUDA graphs
-e2e        the same metric through the public API `env.step(host actions)`: pinned H2D of the actions,
-           the fused step, D2H of observations / rewards / dones, every step (mpe_step_host)
-roofline   achieved = algorithmic bytes per launch (411 B x n_env) / mean launch time
-cpu_baseline  the reference path's per-world NumPy port (oracle/np_port.py), one world per process on all host
-              cores; the C oracle (oracle/mpe_oracle.c) on the same cores is reported under cpu_baseline.c_oracle
+value      device-resident throughput: inputs already in HBM, strictly serialized launches on one stream
+e2e        the same metric through the public API `env.step(pinned host tensors)`: H2D of the actions, the
+           fused step, D2H of observations / rewards / dones, stream synchronize -- every step
+roofline   achieved = algorithmic bytes per launch / mean launch time; `traffic` = DRAM bytes
+           per launch measured in steady state with ncu (tools/traffic.py, profiles/traffic.json), null if this
+           config was not measured; `kernel_ns` = one isolated launch (cold L2) between two events;
+           `size_matched_stream` = a pure streaming kernel with the same read / write byte counts in the same harness
+cpu_baseline  the reference path on the host cores beside the GPU number (N=1): oracle/np_port.py, the per-world
+           NumPy port at the reference's granularity (kind "port"), or the unmodified reference itself when a
+           reference install is present under baseline/_ref (kind "reference")
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -37,28 +49,55 @@ for _v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-SCENARIO = "simple_spread"
-N_ENV = 65536
 EPISODE = 25
 L2_BYTES = 126 * 1024 * 1024
 METRIC = "env_steps_per_sec"
 UNIT = "env-steps/s"
+REF_CHUNK = 100     # reference arm: one bench "step" = REF_CHUNK env.step calls in each process's world
 
 
-SCENARIO_KW = {}
-BYTES_PER_ENV_STEP = 411
-N_AGENTS = 3
+# ------------------------------------------------------------------------------------------------
+# workload description (identical for both arms, computed without touching the CUDA library)
+# ------------------------------------------------------------------------------------------------
+def scenario_world(scenario, kw):
+    from multiagent_particle_envs_b200 import scenarios
+    return scenarios.load(scenario + ".py").Scenario(**kw).make_world()
 
 
-def workload_config(n_gpus, ring):
-    headline = (SCENARIO == "simple_spread" and N_ENV == 65536 and not SCENARIO_KW)
+def shapes_from_oracle(desc):
+    """(act_dims, obs_dims, algorithmic bytes per env-step, input bytes per env-step) from the descriptor and
+    the CPU oracle's shape functions -- the formula of mpe_bytes_per_env_step (csrc/mpe_kernels.cu), restated
+    here so that the CPU arm never has to dlopen libmpe_b200.so; tests/test_cpu_host_logic.py keeps them equal."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from oracle import Oracle
+    o = Oracle(desc, "f64")
+    A, L, C = desc.n_agents, desc.n_landmarks, desc.dim_c
+    S = sum(0 if desc.agent_silent[i] else 1 for i in range(A))
+    G = {4: 1, 5: 1, 6: 1, 7: 2, 8: 2}.get(int(desc.scenario), 0)
+    unread = {8: 4 * A + 2 * L, 6: 4}.get(int(desc.scenario), 0)
+    mov = sum(4 for i in range(A) if desc.agent_movable[i])
+    floats = 4 * A + 2 * L + G + A + S * C - unread + sum(o.act_dims) + sum(o.obs_dims) + mov
+    in_floats = 4 * A + 2 * L + G - unread + sum(o.act_dims)
+    return list(o.act_dims), list(o.obs_dims), 4 * floats + A, 4 * in_floats
+
+
+def ring_size(input_bytes_per_env, n_env, requested=0):
+    need = int(2 * L2_BYTES / (input_bytes_per_env * n_env)) + 1
+    return max(3, need, requested or 0)
+
+
+def workload_config(scenario, kw, n_env, n_agents, bytes_per_env, input_bytes_per_env, n_gpus, ring):
+    headline = (scenario == "simple_spread" and n_env == 65536 and not kw)
     return {"workload": ("simple_spread N=3 agents/landmarks, batch=65536 worlds per GPU (BASELINE configs[1])" if headline
-                         else "%s %s, batch=%d worlds per GPU" % (SCENARIO, SCENARIO_KW or "", N_ENV)),
-            "scenario": SCENARIO, "n_env_per_gpu": N_ENV, "global_n_env": N_ENV * n_gpus,
-            "agents": N_AGENTS, "episode_length": EPISODE, "ring_batches": ring,
-            "l2_policy": ("inputs larger than L2: steps rotate over %d independent batches (%.0f MB > 2x126 MB)"
-                          % (ring, ring * N_ENV * BYTES_PER_ENV_STEP / 1e6)) if ring > 1 else "n/a (CPU arm)",
-            "actions": "softmax of N(0,1) logits, pre-generated per batch, resident in HBM",
+                         else "%s %s, batch=%d worlds per GPU" % (scenario, kw or "", n_env)),
+            "scenario": scenario, "scenario_kwargs": kw, "n_env_per_gpu": n_env, "global_n_env": n_env * n_gpus,
+            "agents": n_agents, "episode_length": EPISODE, "ring_batches": ring,
+            "bytes_per_env_step": bytes_per_env, "input_bytes_per_env_step": input_bytes_per_env,
+            "l2_policy": "inputs larger than L2: steps rotate over %d independent batches; their INPUTS alone (state + "
+                         "actions, %.1f MB per batch) total %.0f MB > 2 x 126 MB L2, all bytes %.0f MB"
+                         % (ring, input_bytes_per_env * n_env / 1e6, ring * input_bytes_per_env * n_env / 1e6,
+                            ring * bytes_per_env * n_env / 1e6),
+            "actions": "softmax of N(0,1) logits (+ uniform utterances), pre-generated per batch, resident in HBM",
             "parallelism": "dp%d (independent shards, no data-path collective)" % n_gpus}
 
 
@@ -70,6 +109,19 @@ def measured_peak():
         except Exception:  # noqa: BLE001
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_key(scenario, kw, n_env):
+    return "%s%s:%d" % (scenario, "".join(",%s=%s" % (k, kw[k]) for k in sorted(kw)), n_env)
+
+
+def measured_traffic(scenario, kw, n_env):
+    """steady-state DRAM bytes per launch of THIS config from profiles/traffic.json (tools/traffic.py + ncu), or None"""
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(tp)).get("steady_state", {}).get(traffic_key(scenario, kw, n_env))
+    except Exception:  # noqa: BLE001
+        return None
 
 
 class ClockSampler(object):
@@ -112,44 +164,92 @@ class ClockSampler(object):
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm.  Two ports of the reference path live under oracle/ (test + baseline infrastructure):
-#   np_port.py     per-world NumPy float64, the reference's own granularity (one world per process) --
-#                  the stand-in for "the reference's own NumPy path"; measured next to the real reference in the
-#                  build container it is 1.1-1.5x FASTER than it (tools/compare_reference_speed.py,
-#                  profiles/r1_cpu_reference_vs_port.json), i.e. a conservative baseline
-#   mpe_oracle.c   the C checker; ~300x faster than the reference itself; reported alongside
+# CPU arm (test / baseline infrastructure under oracle/):
+#   the unmodified reference   when a reference install exists under baseline/_ref (kind "reference")
+#   np_port.py                 per-world NumPy float64 at the reference's own granularity, one world per process --
+#                              the stand-in that can travel to the GPU box (kind "port"); next to the real reference in
+#                              the build container it is 1.1-1.5x FASTER (profiles/r1_cpu_reference_vs_port.json)
+#   mpe_oracle.c               the C checker, ~300x faster than the reference; reported alongside (headline config)
 # ------------------------------------------------------------------------------------------------
-def _spread_desc():
-    from multiagent_particle_envs_b200 import make_env
-    return make_env(SCENARIO, **SCENARIO_KW).world.descriptor()
+def reference_install():
+    p = os.path.join(ROOT, "baseline", "_ref")
+    return p if os.path.isfile(os.path.join(p, "multiagent", "environment.py")) else None
 
 
-def _best_process_count(desc):
+def _ref_worker(args):
+    """one process = one world of the UNMODIFIED reference (baseline/_ref), same action distribution as np_port"""
+    ref_root, name, n_agents, seed, warmup, steps = args
+    import numpy as np
+    os.environ["MPE_REFERENCE_ROOT"] = ref_root
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import refshim
+    np.random.seed(seed)
+    env = refshim.make_reference_env(name, n_agents if name == "simple_spread" else None)
+    env.reset()
+    dims = [int(s.n) if hasattr(s, "n") else int(sum(s.high - s.low + 1)) for s in env.action_space]
+    mov = [bool(a.movable) for a in env.world.agents]
+    rng = np.random.RandomState(seed)
+
+    def acts():
+        out = []
+        for d, m in zip(dims, mov):
+            parts = []
+            if m:
+                z = rng.randn(5)
+                e = np.exp(z - z.max())
+                parts.append(e / e.sum())
+            if d - (5 if m else 0) > 0:
+                parts.append(rng.uniform(0, 1, d - (5 if m else 0)))
+            out.append(np.concatenate(parts))
+        return out
+
+    for _ in range(warmup):
+        env.step(acts())
+    t0 = time.perf_counter()
+    for t in range(steps):
+        if t % EPISODE == 0:
+            env.reset()
+        env.step(acts())
+    return steps / (time.perf_counter() - t0)
+
+
+def _cpu_throughput(desc, scenario, kw, procs, warmup, steps, shared_reward):
+    """aggregate env-steps/s of `procs` processes x one world each; (total, kind)"""
+    ref = reference_install()
+    if ref is not None:
+        import multiprocessing as mp
+        n_agents = kw.get("num_agents")
+        with mp.get_context("fork").Pool(procs) as pool:
+            rates = pool.map(_ref_worker, [(ref, scenario, n_agents, 100 + p, warmup, steps) for p in range(procs)])
+        return float(sum(rates)), "reference"
+    import np_port
+    total, _ = np_port.timed_throughput(desc, procs, warmup, steps, shared_reward=shared_reward)
+    return total, "port"
+
+
+def _best_process_count(desc, scenario, kw, shared):
     """`os.sched_getaffinity` can exceed what the container may really use (CPU quota, SMT): probe a few process
     counts briefly and keep the one with the highest aggregate throughput -- "all the host threads it can use"."""
-    import np_port
     cores = len(os.sched_getaffinity(0))
     cands = sorted({max(1, cores // 8), max(1, cores // 4), max(1, cores // 2), cores})
     best = (0.0, cores)
     for p in cands:
-        rate, _ = np_port.timed_throughput(desc, p, 10, 150)
+        rate, _ = _cpu_throughput(desc, scenario, kw, p, 10, 150, shared)
         if rate > best[0]:
             best = (rate, p)
     return best[1], best[0]
 
 
-def cpu_numpy_port(budget_s, steps=None, warmup=100, max_seconds=None):
+def cpu_reference_path(desc, scenario, kw, shared, steps, warmup, max_seconds):
+    """times the reference path: `steps` env.step calls per process after `warmup` (both may shrink to fit
+    max_seconds of wall time, never below 500 / 50)"""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import np_port
-    desc = _spread_desc()
-    procs, probe = _best_process_count(desc)
-    per_proc = probe / procs
-    if steps is None:
-        steps = int(max(200, min(20000, budget_s * per_proc)))
-    if max_seconds is not None:
-        steps = int(max(50, min(steps, max_seconds * per_proc)))
+    procs, probe = _best_process_count(desc, scenario, kw, shared)
+    per_proc = max(probe / procs, 1.0)
+    steps = int(max(500, min(steps, max_seconds * per_proc)))
+    warmup = int(max(50, min(warmup, 0.25 * max_seconds * per_proc)))
     t0 = time.perf_counter()
-    total, rates = np_port.timed_throughput(desc, procs, warmup, steps)
+    total, kind = _cpu_throughput(desc, scenario, kw, procs, warmup, steps, shared)
     dt = time.perf_counter() - t0
     cpu_model = ""
     try:
@@ -159,22 +259,22 @@ def cpu_numpy_port(budget_s, steps=None, warmup=100, max_seconds=None):
                 break
     except OSError:
         pass
-    return {"value": total, "unit": UNIT, "cores": procs, "kind": "port", "cpu_model": cpu_model,
-            "sample": "%d processes (best of the probed counts; affinity reports %d CPUs) x %d env.step calls of one "
-                      "%s world each (oracle/np_port.py: per-world NumPy float64 restatement at the reference's "
-                      "granularity, softmax actions, reset every 25 steps); %.1f s wall"
-                      % (procs, len(os.sched_getaffinity(0)), steps, SCENARIO, dt),
-            "per_process": total / procs, "steps_per_process": steps, "seconds": dt}
+    what = ("the UNMODIFIED reference (baseline/_ref, MultiAgentEnv.step, environment.py:80-104)" if kind == "reference"
+            else "oracle/np_port.py (per-world NumPy float64 restatement at the reference's granularity)")
+    return {"value": total, "unit": UNIT, "cores": procs, "kind": kind, "cpu_model": cpu_model,
+            "sample": "%d processes (best of the probed counts; affinity reports %d CPUs) x %d env.step calls of one %s "
+                      "world each after %d warm-up calls, through %s; softmax actions, reset every 25 steps; %.1f s wall"
+                      % (procs, len(os.sched_getaffinity(0)), steps, scenario, warmup, what, dt),
+            "per_process": total / procs, "steps_timed_per_process": steps, "warmup_per_process": warmup, "seconds": dt}
 
 
-def cpu_c_oracle(budget_s, n_sample=N_ENV):
-    """env-steps/s of oracle/mpe_oracle.c (fp64) stepping n_sample worlds split over all host threads; the
-    step loop runs inside C (ctypes releases the GIL)."""
+def cpu_c_oracle(desc, budget_s, n_sample=65536):
+    """env-steps/s of oracle/mpe_oracle.c (fp64) stepping n_sample simple_spread worlds split over all host threads;
+    the step loop runs inside C (ctypes releases the GIL).  Headline config only."""
     import numpy as np
     from concurrent.futures import ThreadPoolExecutor
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     from oracle import Oracle
-    desc = _spread_desc()
     cores = len(os.sched_getaffinity(0))
     rng = np.random.RandomState(0)
     A, L = 3, 3
@@ -206,52 +306,270 @@ def cpu_c_oracle(budget_s, n_sample=N_ENV):
                       "per core); %.1f s" % (steps, n_sample, dt)}
 
 
-def cpu_baseline_block(numpy_seconds, c_seconds):
-    cb = cpu_numpy_port(numpy_seconds)
-    out = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "cpu_model")}
-    out["per_process"] = cb["per_process"]
-    if c_seconds > 0:
-        c = cpu_c_oracle(c_seconds)
+def cpu_baseline_block(desc, scenario, kw, shared, seconds, headline):
+    cb = cpu_reference_path(desc, scenario, kw, shared, steps=20000, warmup=100, max_seconds=seconds)
+    out = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "cpu_model", "per_process",
+                              "steps_timed_per_process")}
+    if headline:
+        c = cpu_c_oracle(desc, 5.0)
         out["c_oracle"] = {k: c[k] for k in ("value", "unit", "cores", "sample")}
-    return out, cb
+    return out
 
 
 def run_reference_arm(args, rank, world):
-    """The reference's CPU path on this box's host cores: the per-world NumPy port, one world per process
-    on every core.  One bench "step" here = one env.step in each of the `cores` worlds (a bounded sample of
-    the 65536-world batch); the timed run is capped at ~90 s."""
+    """The reference's CPU path on this box's host cores, one world per process on every core.  One bench "step"
+    of this arm = REF_CHUNK env.step calls in each process's world (a bounded sample of the n_env-world batch):
+    `--steps 20 --warmup 5` times 2000 calls per process after 500 warm-up calls.  Loads neither CUDA nor
+    libmpe_b200.so: shapes come from the descriptor and the CPU oracle."""
     if rank != 0:
         return
     t_all = time.perf_counter()
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    res = cpu_numpy_port(0, steps=args.steps, warmup=min(max(args.warmup, 3), 300), max_seconds=75.0)
-    steps_timed = res["steps_per_process"]
-    cores = res["cores"]
-    cb = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "cpu_model")}
-    cb["per_process"] = res["per_process"]
-    if SCENARIO == "simple_spread" and not SCENARIO_KW:
-        c = cpu_c_oracle(5.0)
+    import __graft_entry__ as g
+    g.build_oracle(quiet=True)
+    w = scenario_world(args.scenario, args.scenario_kw)
+    desc = w.descriptor()
+    shared = bool(getattr(w, "collaborative", False))
+    act_dims, obs_dims, bpe, ibpe = shapes_from_oracle(desc)
+    ring = ring_size(ibpe, args.num_envs, args.ring)
+    res = cpu_reference_path(desc, args.scenario, args.scenario_kw, shared,
+                             steps=max(2000, args.steps * REF_CHUNK), warmup=max(100, args.warmup * REF_CHUNK),
+                             max_seconds=90.0)
+    cb = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "cpu_model", "per_process",
+                              "steps_timed_per_process", "warmup_per_process")}
+    headline = args.scenario == "simple_spread" and not args.scenario_kw
+    if headline:
+        c = cpu_c_oracle(desc, 5.0)
         cb["c_oracle"] = {k: c[k] for k in ("value", "unit", "cores", "sample")}
+    cores = res["cores"]
+    per_step_calls = res["steps_timed_per_process"] / float(args.steps)
     line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "steps_timed_per_process": steps_timed, "warmup": args.warmup,
-            "ms_per_step": 1e3 * cores / res["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": workload_config(args.gpus, 1), "cpu_baseline": cb,
-            "agent_steps_per_sec": 3 * res["value"],
+            "steps": args.steps, "warmup": args.warmup, "steps_timed_per_process": res["steps_timed_per_process"],
+            "ms_per_step": 1e3 * per_step_calls * cores / res["value"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.scenario, args.scenario_kw, args.num_envs, desc.n_agents, bpe, ibpe, args.gpus, ring),
+            "cpu_baseline": cb, "agent_steps_per_sec": desc.n_agents * res["value"],
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t_all,
-            "note": "reference arm = oracle/np_port.py, the per-world NumPy port of the reference path (the Python reference "
-                    "itself cannot travel to the GPU box); %d processes, one world each; the C oracle on the same cores is "
-                    "reported under cpu_baseline.c_oracle" % cores}
+            "native_so_in_process": sorted({ln.split()[-1][len(ROOT) + 1:] for ln in open("/proc/self/maps")
+                                            if ln.rstrip().endswith(".so") and ROOT in ln}),
+            "note": "reference arm = the reference's CPU path on the host cores (%s): %d processes, one world each, %d "
+                    "env.step calls per process = %d bench steps of %.0f calls; it does not scale with --gpus"
+                    % ("the unmodified reference from baseline/_ref" if res["kind"] == "reference" else
+                       "oracle/np_port.py, the per-world NumPy port -- the Python reference itself cannot travel to the GPU box",
+                       cores, res["steps_timed_per_process"], args.steps, per_step_calls)}
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def pin_to_gpu_numa(local_rank):
+    """Bind this rank to the CPUs of its GPU's NUMA node BEFORE CUDA starts and before any pinned slab is allocated
+    (first touch puts the staging buffers on that node; torch.distributed.run does not bind).  Returns the original
+    affinity (restored for the CPU baseline) and a description."""
+    orig = os.sched_getaffinity(0)
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=index,pci.bus_id", "--format=csv,noheader"], capture_output=True,
+                             text=True, timeout=20).stdout
+        bus = None
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[local_rank]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else local_rank
+        for ln in out.splitlines():
+            idx, b = [x.strip() for x in ln.split(",")]
+            if int(idx) == phys:
+                bus = b.lower()
+        if bus is None:
+            return orig, "no pci bus id"
+        if len(bus.split(":")[0]) == 8:       # nvidia-smi prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        if node < 0:
+            return orig, "single NUMA node"
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= orig
+        if not cpus:
+            return orig, "NUMA node %d has no allowed CPU" % node
+        os.sched_setaffinity(0, cpus)
+        return orig, "NUMA node %d (%d CPUs)" % (node, len(cpus))
+    except Exception as e:  # noqa: BLE001
+        return orig, "not pinned (%s)" % type(e).__name__
+
+
+class Ring(object):
+    """R independent env batches with resident actions and outputs + the CUDA-graph plans that step them"""
+
+    def __init__(self, scenario, kw, n_env, dev, rank, world, requested_ring=0):
+        import torch
+        from multiagent_particle_envs_b200 import _lib, make_env
+        self.torch, self.dev, self.n_env = torch, dev, n_env
+        probe = make_env(scenario, **kw)
+        sh = probe.world.native_shapes()
+        self.n_agents = probe.n
+        self.bytes_per_env = sh.bytes_per_env_step
+        mov = [bool(a.movable) for a in probe.agents]
+        A, L = sh.n_agents, sh.n_landmarks
+        unread = {_lib.SCN_CRYPTO: 4 * A + 2 * L, _lib.SCN_SPEAKER_LISTENER: 4}.get(int(sh.desc.scenario), 0)
+        self.input_bytes_per_env = 4 * (4 * A + 2 * L + sh.n_goals - unread + sum(sh.act_dims))
+        self.R = ring_size(self.input_bytes_per_env, n_env, requested_ring)
+        self.bytes_per_step = self.bytes_per_env * n_env
+        self.slots = []
+        for b in range(self.R):
+            env = make_env(scenario, num_envs=n_env * world, device=dev, seed=1000 + b, rank=rank, world_size=world, **kw)
+            env.reset()
+            nw = env.world.native
+            g = torch.Generator(device=dev).manual_seed(7 * b + rank)
+            acts = []
+            for d_act, m in zip(nw.act_dims, mov):     # 5 movement probabilities, then the utterance
+                parts = []
+                if m:
+                    parts.append(torch.softmax(torch.randn(n_env, 5, device=dev, generator=g), 1))
+                if d_act - (5 if m else 0) > 0:
+                    parts.append(torch.rand(n_env, d_act - (5 if m else 0), device=dev, generator=g))
+                acts.append(torch.cat(parts, 1).contiguous())
+            self.slots.append((env, nw, acts, _lib.ptr_array([t.data_ptr() for t in acts]), env._flags()))
+        self.unit = self.R * EPISODE
+        self.stream = torch.cuda.Stream(dev)
+        self.side = torch.cuda.Stream(dev)
+        self.launches = 0
+        self._graphs = {}
+        with torch.cuda.stream(self.stream):
+            for i in range(self.R):      # first launches outside capture (module load, lazy init)
+                self.step_slot(i)
+            self.stream.synchronize()
+        self.launches = 0
+
+    def step_slot(self, i):
+        env, nw, acts, ptrs, flags = self.slots[i % self.R]
+        nw.step(ptrs, nw.out, flags)
+        self.launches += 1
+
+    def reset_all(self):
+        for env, nw, acts, ptrs, flags in self.slots:
+            nw.reset()
+            self.launches += 1
+
+    def _capture(self, first, count, two_streams):
+        """one CUDA graph stepping slots first .. first+count-1 (mod R), strictly in order on one stream, or with
+        even / odd positions on two streams (fork / join) for the two-batches-in-flight extra"""
+        key = (first % self.R, count, two_streams)
+        if key in self._graphs:
+            return self._graphs[key]
+        torch = self.torch
+        before = self.launches
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=self.stream):
+            if two_streams:
+                self.side.wait_stream(self.stream)
+            for k in range(count):
+                if two_streams and k % 2:
+                    with torch.cuda.stream(self.side):
+                        self.step_slot(first + k)
+                else:
+                    self.step_slot(first + k)
+            if two_streams:
+                self.stream.wait_stream(self.side)
+        self.launches = before      # capture is not execution
+        self._graphs[key] = graph
+        return graph
+
+    def plan(self, k, two_streams=False):
+        """graphs covering exactly k steps: whole units (R x 25 steps, then the episode resets) + one remainder"""
+        units, rem = divmod(k, self.unit)
+        return (self._capture(0, self.unit, two_streams) if units else None, units,
+                self._capture(0, rem, two_streams) if rem else None, rem)
+
+    def run(self, plan):
+        unit_graph, units, rem_graph, rem = plan
+        for _ in range(units):
+            unit_graph.replay()
+            self.launches += self.unit
+            self.reset_all()
+        if rem:
+            rem_graph.replay()
+            self.launches += rem
+
+    def timed(self, plan, spin_cycles):
+        """seconds of device time for one run of `plan`, measured between two events on the launching stream; a spin
+        kernel ahead of the start event absorbs the host's enqueue latency"""
+        torch = self.torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(self.stream):
+            torch.cuda._sleep(spin_cycles)
+            e0.record(self.stream)
+            self.run(plan)
+            e1.record(self.stream)
+            self.stream.synchronize()
+        return e0.elapsed_time(e1) / 1e3
+
+    def isolated_kernel_ns(self, spin_cycles, repeats=9):
+        """one fused-step launch between two events, L2 flushed by a 256 MB fill before each: median / min in ns"""
+        torch = self.torch
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=self.dev)
+        out = []
+        with torch.cuda.stream(self.stream):
+            for r in range(repeats):
+                flush.fill_(r)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda._sleep(spin_cycles)
+                e0.record(self.stream)
+                self.step_slot(r)
+                e1.record(self.stream)
+                self.stream.synchronize()
+                out.append(e0.elapsed_time(e1) * 1e6)
+        self.launches -= repeats
+        out.sort()
+        return {"median": out[len(out) // 2], "min": out[0], "repeats": repeats,
+                "note": "event pair around ONE launch on an idle GPU with a flushed L2 (includes launch + drain)"}
+
+    def size_matched_stream(self, lib, k, spin_cycles):
+        """the same harness around a pure streaming kernel with this config's read / write byte counts per launch"""
+        torch = self.torch
+        rd = (self.input_bytes_per_env * self.n_env + 15) // 16 * 16
+        wr = ((self.bytes_per_env - self.input_bytes_per_env) * self.n_env + 15) // 16 * 16
+        src = torch.zeros(self.R * rd // 4, dtype=torch.float32, device=self.dev)
+        dst = torch.empty(self.R * wr // 4, dtype=torch.float32, device=self.dev)
+        threads = max(256, self.n_env)
+        import ctypes
+
+        def probe(i):
+            rc = lib.mpe_probe_stream(self.dev.index, ctypes.c_void_p(src.data_ptr() + (i % self.R) * rd), rd,
+                                      ctypes.c_void_p(dst.data_ptr() + (i % self.R) * wr), wr, threads,
+                                      ctypes.c_void_p(self.stream.cuda_stream))
+            if rc:
+                raise RuntimeError("mpe_probe_stream failed: %d" % rc)
+
+        k = max(1, min(k, self.unit))
+        with torch.cuda.stream(self.stream):
+            for i in range(self.R):
+                probe(i)
+            self.stream.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=self.stream):
+                for i in range(k):
+                    probe(i)
+            graph.replay()
+            self.stream.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda._sleep(spin_cycles)
+            e0.record(self.stream)
+            graph.replay()
+            e1.record(self.stream)
+            self.stream.synchronize()
+        sec = e0.elapsed_time(e1) / 1e3 / k
+        return {"ms_per_launch": 1e3 * sec, "gbs": (rd + wr) / sec / 1e9, "launches": k, "read_bytes": rd, "write_bytes": wr,
+                "note": "pure streaming kernel (float4 loads, then dependent evict-first float4 stores), one thread per world, "
+                        "same launch path / graph replay / ring rotation: what this batch size allows a strictly "
+                        "serialized launch to reach"}
+
+
 def run_b200_arm(args, rank, local_rank, world):
+    orig_affinity, numa = pin_to_gpu_numa(local_rank)
     import torch
     import torch.distributed as dist
-    from multiagent_particle_envs_b200 import _lib, make_env
+    from multiagent_particle_envs_b200 import _lib
     from multiagent_particle_envs_b200.sharding import aggregate_counters
 
     torch.cuda.set_device(local_rank)
@@ -271,140 +589,81 @@ def run_b200_arm(args, rank, local_rank, world):
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
     lib = _lib.load()
+    N_ENV = args.num_envs
+    ring = Ring(args.scenario, args.scenario_kw, N_ENV, dev, rank, world, args.ring)
+    R = ring.R
+    K, W = args.steps, max(args.warmup, 3)
+    sm_hz = getattr(torch.cuda.get_device_properties(dev), "clock_rate", 1.9e6) * 1e3      # kHz -> Hz
+    spin = int(200e-6 * sm_hz)      # ~200 us of spinning in front of every timed region
 
-    # ---- ring of independent batches, each with resident actions and outputs -------------------
-    bytes_per_step = None
-    ring = []
-    R = args.ring
-    for b in range(R):
-        env = make_env(SCENARIO, num_envs=N_ENV * world, device=dev, seed=1000 + b, rank=rank, world_size=world,
-                       **SCENARIO_KW)
-        env.reset()
-        nw = env.world.native
-        bytes_per_step = nw.bytes_per_env_step * N_ENV
-        g = torch.Generator(device=dev).manual_seed(7 * b + rank)
-        acts = []
-        for d_act, ag in zip(nw.act_dims, env.agents):     # 5 movement probabilities, then the utterance
-            parts = []
-            if ag.movable:
-                parts.append(torch.softmax(torch.randn(N_ENV, 5, device=dev, generator=g), 1))
-            if d_act - (5 if ag.movable else 0) > 0:
-                parts.append(torch.rand(N_ENV, d_act - (5 if ag.movable else 0), device=dev, generator=g))
-            acts.append(torch.cat(parts, 1).contiguous())
-        ring.append((env, nw, acts, _lib.ptr_array([t.data_ptr() for t in acts]), env._flags()))
-    if R * bytes_per_step <= 2 * L2_BYTES:
-        raise SystemExit("ring working set (%d x %.0f MB) must exceed 2x L2: raise --ring" % (R, bytes_per_step / 1e6))
-    stream = torch.cuda.Stream(dev)
-    launches = [0]
-
-    def step_ring_once():
-        for env, nw, acts, ptrs, flags in ring:
-            nw.step(ptrs, nw.out, flags)
-            launches[0] += 1
-
-    def reset_ring():
-        for env, nw, acts, ptrs, flags in ring:
-            nw.reset()
-            launches[0] += 1
-
-    unit_steps = R * EPISODE
-    with torch.cuda.stream(stream):
-        step_ring_once()  # first launches outside capture (module load)
-        stream.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        l0 = launches[0]
-        with torch.cuda.graph(graph, stream=stream):
-            for _ in range(EPISODE):
-                step_ring_once()
-        launches[0] = l0  # capture is not execution
-
-        def run_steps(k):
-            """exactly k fused steps: whole episodes from the graph (+ the episode resets), then the rest"""
-            units, rem = divmod(k, unit_steps)
-            for _ in range(units):
-                graph.replay()
-                launches[0] += unit_steps
-                reset_ring()
-            i = 0
-            while rem > 0:
-                env, nw, acts, ptrs, flags = ring[i % R]
-                nw.step(ptrs, nw.out, flags)
-                launches[0] += 1
-                i += 1
-                rem -= 1
-
-        run_steps(max(args.warmup, 3))
-        stream.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        sampler = ClockSampler(local_rank).start()
-        time.sleep(0.12)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        launches[0] = 0
-        t0 = time.time()
-        e0.record(stream)
-        run_steps(args.steps)
-        e1.record(stream)
-        stream.synchronize()
-        t1 = time.time()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        clocks = sampler.stop(t0, t1)
-        seconds = e0.elapsed_time(e1) / 1e3
-        # extra (not the headline): the same K steps with TWO batches in flight -- even ring slots on one stream,
-        # odd ones on another, captured as a fork/join graph -- so that a step's launch latency, ramp-up and
-        # store drain overlap the neighbouring batch's step.  Each batch still advances strictly in order.
-        side = torch.cuda.Stream(dev)
-        graph2 = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph2, stream=stream):
-            side.wait_stream(stream)
-            for _ in range(EPISODE):
-                for slot, (env_s, nw_s, acts_s, ptrs_s, flags_s) in enumerate(ring):
-                    with torch.cuda.stream(side if slot % 2 else stream):
-                        nw_s.step(ptrs_s, nw_s.out, flags_s)
-            stream.wait_stream(side)
-        units2 = max(1, args.steps // unit_steps)
-        for _ in range(2):
-            graph2.replay()
-        stream.synchronize()
-        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e2.record(stream)
-        for _ in range(units2):
-            graph2.replay()
-        e3.record(stream)
-        stream.synchronize()
-        seconds2 = e2.elapsed_time(e3) / 1e3
-    gpu_launches = launches[0]
-    total_steps, max_seconds, per_rank = aggregate_counters(N_ENV * args.steps, seconds)
-    total2, max2, _ = aggregate_counters(N_ENV * units2 * unit_steps, seconds2)
-    value = total_steps / max_seconds
-
-    # ---- end to end through the public API with host buffers ------------------------------------
-    env, nw = ring[0][0], ring[0][1]
-    k_e2e = max(3, min(args.steps, args.e2e_steps))
-    host_acts = [[a.cpu().pin_memory() for a in ring[b % R][2]] for b in range(4)]
-    h2d = sum(a.numel() * 4 for a in host_acts[0])
-    for b in range(3):
-        obs_n, rew_n, done_n, _ = env.step(host_acts[b % 4])
-    d2h = sum(o.numel() * 4 for o in obs_n) + sum(r.numel() * 4 for r in rew_n) + sum(d.numel() for d in done_n)
+    # ---- value: exactly K strictly serialized steps, replayed from graphs captured beforehand ------------------
+    plan = ring.plan(K)
+    warm_plan = ring.plan(W)
+    with torch.cuda.stream(ring.stream):
+        ring.run(warm_plan)                       # the W warm-up steps
+        ring.run(ring.plan(K if K <= ring.unit else ring.unit + K % ring.unit))   # + one untimed replay of every timed graph
+        ring.stream.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank).start()
+    time.sleep(0.12)
+    ring.launches = 0
+    t0 = time.time()
+    seconds = ring.timed(plan, spin)
+    t1 = time.time()
+    gpu_launches = ring.launches
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    checksum = 0.0
-    w0 = time.perf_counter()
-    for b in range(k_e2e):
-        obs_n, rew_n, done_n, _ = env.step(host_acts[b % 4])   # H2D + fused step + D2H + sync inside
-        checksum += float(rew_n[0][0])                          # the caller reads the result on the host
-    torch.cuda.synchronize()
-    e2e_seconds = time.perf_counter() - w0
-    e2e_total, e2e_max, _ = aggregate_counters(N_ENV * k_e2e, e2e_seconds)
-    e2e_value = e2e_total / e2e_max
+    clocks = sampler.stop(t0, t1)
+    total_steps, max_seconds, per_rank = aggregate_counters(N_ENV * K, seconds)
+    value = total_steps / max_seconds
+
+    # ---- extras on the same K steps: two batches in flight; isolated launch; size-matched streaming kernel ----
+    plan2 = ring.plan(K, two_streams=True)
+    with torch.cuda.stream(ring.stream):
+        ring.run(ring.plan(K if K <= ring.unit else ring.unit + K % ring.unit, two_streams=True))
+        ring.stream.synchronize()
+    seconds2 = ring.timed(plan2, spin)
+    total2, max2, _ = aggregate_counters(N_ENV * K, seconds2)
+    kernel_ns = ring.isolated_kernel_ns(spin) if rank == 0 else None
+    probe = ring.size_matched_stream(lib, K, spin) if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+
+    # ---- end to end through the public API with host buffers --------------------------------------------------
+    env = ring.slots[0][0]
+    k_e2e = max(3, min(K, args.e2e_steps))
+    host_acts = [[a.cpu().pin_memory() for a in ring.slots[b % R][2]] for b in range(4)]
+    h2d = sum(a.numel() * 4 for a in host_acts[0])
+
+    def e2e_run(e, reuse):
+        e.reuse_buffers = reuse
+        for b in range(3):
+            obs_n, rew_n, done_n, _ = e.step(host_acts[b % 4])
+        nbytes = sum(o.numel() * 4 for o in obs_n) + sum(r.numel() * 4 for r in rew_n) + sum(d.numel() for d in done_n)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        chk = 0.0
+        w0 = time.perf_counter()
+        for b in range(k_e2e):
+            obs_n, rew_n, done_n, _ = e.step(host_acts[b % 4])   # H2D + fused step + D2H + sync inside
+            chk += float(rew_n[0][0])                            # the caller reads the result on the host
+        torch.cuda.synchronize()
+        sec = time.perf_counter() - w0
+        tot, mx, _ = aggregate_counters(N_ENV * k_e2e, sec)
+        return tot / mx, mx, nbytes, chk
+
+    e2e_value, e2e_max, d2h, checksum = e2e_run(env, True)
+    fresh_value, fresh_max, _, _ = e2e_run(env, False)
+    env.reuse_buffers = True
 
     # extra (not the headline): two env batches in flight through step_async / step_wait, so that the upload +
     # step of one overlaps the download of the other -- what a double-buffered host trainer would see
-    env_b = ring[1][0]
+    env_b = ring.slots[1][0]
+    env_b.reuse_buffers = True
     lanes = {id(env): torch.cuda.Stream(dev), id(env_b): torch.cuda.Stream(dev)}   # one stream per env batch
 
     def launch(e, acts):
@@ -428,36 +687,48 @@ def run_b200_arm(args, rank, local_rank, world):
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        launch_s = max_seconds / args.steps
-        achieved = bytes_per_step / launch_s / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp) and SCENARIO == "simple_spread" and N_ENV == 65536 and not SCENARIO_KW:
-            try:
-                traffic = json.load(open(tp)).get("simple_spread_65536_dram_bytes_per_launch")
-            except Exception:  # noqa: BLE001
-                traffic = None
+        launch_s = max_seconds / K
+        achieved = ring.bytes_per_step / launch_s / 1e9
+        traffic = measured_traffic(args.scenario, args.scenario_kw, N_ENV)
+        headline = args.scenario == "simple_spread" and not args.scenario_kw
         cpu = None
         if world == 1 and args.cpu_seconds > 0:
-            cpu = cpu_baseline_block(args.cpu_seconds, 5.0 if SCENARIO == "simple_spread" and not SCENARIO_KW else 0.0)[0]
+            os.sched_setaffinity(0, orig_affinity)      # the CPU arm uses every host core
+            w = scenario_world(args.scenario, args.scenario_kw)
+            cpu = cpu_baseline_block(w.descriptor(), args.scenario, args.scenario_kw,
+                                     bool(getattr(w, "collaborative", False)), args.cpu_seconds, headline)
+        probe["frac"] = probe["gbs"] / peak
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": 1e3 * launch_s, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(world, R),
-            "agent_steps_per_sec": N_AGENTS * value,
+            "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.scenario, args.scenario_kw, N_ENV, ring.n_agents, ring.bytes_per_env,
+                                      ring.input_bytes_per_env, world, R),
+            "agent_steps_per_sec": ring.n_agents * value,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": k_e2e, "ms_per_step": 1e3 * e2e_max / k_e2e, "api": "MultiAgentEnv.step(pinned host tensors)"},
-            "value_two_batches_in_flight": {"value": total2 / max2, "unit": UNIT, "ms_per_step": 1e3 * max2 / (units2 * unit_steps),
-                                            "frac": bytes_per_step / (max2 / (units2 * unit_steps)) / 1e9 / peak,
-                                            "note": "extra: alternate ring slots on two streams (fork/join CUDA graph)"},
+                    "steps": k_e2e, "ms_per_step": 1e3 * e2e_max / k_e2e,
+                    "api": "MultiAgentEnv.step(pinned host tensors) with env.reuse_buffers = True: results are views of "
+                           "the two flip-flopped pinned result slabs (valid until the next-but-one step)",
+                    "cpu_affinity": numa},
+            "e2e_fresh_arrays": {"value": fresh_value, "unit": UNIT, "ms_per_step": 1e3 * fresh_max / k_e2e,
+                                 "api": "the same call with the default env.reuse_buffers = False: every step hands out "
+                                        "freshly allocated host copies (the reference's ownership semantics)"},
+            "value_two_batches_in_flight": {"value": total2 / max2, "unit": UNIT, "steps": K, "ms_per_step": 1e3 * max2 / K,
+                                            "frac": ring.bytes_per_step / (max2 / K) / 1e9 / peak,
+                                            "note": "extra: the same K steps with alternate ring slots on two streams "
+                                                    "(fork/join CUDA graph); each batch still advances strictly in order"},
             "e2e_two_batches_in_flight": {"value": pipe_total / pipe_max, "unit": UNIT, "ms_per_step": 1e3 * pipe_max / k_e2e,
                                           "api": "step_async / step_wait alternating over two env batches"},
             "gpu_launches": gpu_launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": bytes_per_step,
-                         "kernel": "mpe_kernel<%s program, kFusedStep>" % SCENARIO},
+                         "traffic_source": ("profiles/traffic.json (ncu --cache-control none, steady state over the ring, "
+                                            "tools/traffic.py)" if traffic is not None else "not measured for this config"),
+                         "frac_of_measured_traffic": (traffic / launch_s / 1e9 / peak) if traffic else None,
+                         "algorithmic_bytes_per_launch": ring.bytes_per_step,
+                         "kernel_ns": kernel_ns, "size_matched_stream": probe,
+                         "kernel": "mpe_kernel<%s program, kFusedStep>" % args.scenario},
             "per_rank": per_rank,
         }
         if cpu is not None:
@@ -467,42 +738,39 @@ def run_b200_arm(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
-def main():
+def parse_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=60000)
     ap.add_argument("--warmup", type=int, default=3000)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--ring", type=int, default=12)
+    ap.add_argument("--ring", type=int, default=0, help="ring batches (default: sized so that the inputs exceed 2x L2)")
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--scenario", default="simple_spread", help="other BASELINE configs: simple_tag, simple_world_comm, ...")
     ap.add_argument("--num-envs", type=int, default=65536, help="worlds per GPU")
     ap.add_argument("--num-agents", type=int, default=None, help="simple_spread only (N agents = N landmarks)")
-    args = ap.parse_args()
-    global SCENARIO, N_ENV, SCENARIO_KW, BYTES_PER_ENV_STEP, N_AGENTS
-    SCENARIO, N_ENV = args.scenario, args.num_envs
-    if args.num_agents is not None:
-        SCENARIO_KW = {"num_agents": args.num_agents}
-    from multiagent_particle_envs_b200 import make_env as _mk
-    _probe = _mk(SCENARIO, **SCENARIO_KW)
-    BYTES_PER_ENV_STEP, N_AGENTS = _probe.world.native_shapes().bytes_per_env_step, _probe.n
-    if args.ring * N_ENV * BYTES_PER_ENV_STEP <= 2 * L2_BYTES:
-        args.ring = int(2 * L2_BYTES / (N_ENV * BYTES_PER_ENV_STEP)) + 2
+    args = ap.parse_args(argv)
+    args.scenario_kw = {"num_agents": args.num_agents} if args.num_agents is not None else {}
+    return args
+
+
+def main():
+    args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world == 1 and args.gpus > 1 and args.impl == "b200":
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)     # no CUDA, no libmpe_b200.so in this process
+        return
+    if world == 1 and args.gpus > 1:
         # convenience: re-launch under torchrun
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                "--master-addr", "127.0.0.1", "--master-port", str(29400 + os.getpid() % 500), os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
     import __graft_entry__ as g
     g.build(quiet=True)
-    if args.impl == "reference":
-        run_reference_arm(args, rank, world)
-    else:
-        run_b200_arm(args, rank, local_rank, world)
+    run_b200_arm(args, rank, local_rank, world)
 
 
 if __name__ == "__main__":

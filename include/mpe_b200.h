@@ -76,7 +76,10 @@ enum mpe_error {
 enum mpe_step_flags {
     MPE_FLAG_SHARED_REWARD = 1,         /* env.shared_reward: every agent gets sum_i r_i   :100-102 */
     MPE_FLAG_FORCE_DISCRETE_ACTION = 2, /* env.force_discrete_action: argmax one-hot       :169-172 */
-    MPE_FLAG_DISCRETE_ACTION_INPUT = 4, /* env.discrete_action_input: act_n holds indices  :161-167,185-187 */
+    MPE_FLAG_DISCRETE_ACTION_INPUT = 4, /* env.discrete_action_input (:161-167,185-187): act_n[i] is int32
+                                           [n_env][n_sub_i], one index per sub-action -- movement (0 none, 1 -x,
+                                           2 +x, 3 -y, 4 +y) if the agent is movable, then the utterance
+                                           (one-hot of the index) if it is not silent; decoded inside the kernel */
     MPE_FLAG_HOST_SLAB = 8              /* mpe_step_host only: obs_n_host[0..A), rew_host, done_host (, info_host)
                                            are consecutive parts of ONE host allocation and their device
                                            counterparts of ONE device allocation, with equal gaps < 512 B:
@@ -195,6 +198,11 @@ MPE_API const char *mpe_strerror(int err);
 MPE_API const char *mpe_last_cuda_error(void);  /* text of the last CUDA failure on this thread */
 MPE_API int mpe_abi_version(void);
 MPE_API int64_t mpe_kernel_launches(void);      /* kernels launched by this library so far (process-wide) */
+/* Measurement aid (bench.py "size-matched streaming ceiling"): one launch of a pure streaming kernel that reads
+ * read_bytes from src_dev and then writes write_bytes to dst_dev (both 16-byte aligned) with `threads` threads,
+ * through the same launch path as mpe_step.  Not counted by mpe_kernel_launches; computes nothing. */
+MPE_API int mpe_probe_stream(int device, const void *src_dev, int64_t read_bytes, void *dst_dev, int64_t write_bytes,
+                             int64_t threads, void *stream);
 
 #ifdef __cplusplus
 }

@@ -89,6 +89,7 @@ _SIGNATURES = {
     "mpe_last_cuda_error": (ctypes.c_char_p, []),
     "mpe_abi_version": (ctypes.c_int, []),
     "mpe_kernel_launches": (ctypes.c_int64, []),
+    "mpe_probe_stream": (ctypes.c_int, [ctypes.c_int, _P, ctypes.c_int64, _P, ctypes.c_int64, ctypes.c_int64, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

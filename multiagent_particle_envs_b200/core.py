@@ -284,9 +284,12 @@ class World(object):
     def reset_states(self, mask=None, seed=None):
         nw = self.bind() if self._native is None else self._native
         self._needs_reset = False
-        if seed is not None:
-            self.seed = seed
+        if seed is not None:     # (seed, epoch) key the Philox draw: reseeding restarts the epoch, so that
+            self.seed = seed     # env.reset(seed=s) reproduces the same episode every time it is called
             nw.seed = seed
+            nw.epoch = 0
+            if nw._epoch_dev is not None:
+                nw._epoch_dev.zero_()
         nw.reset(mask)
         self._obs_valid = False
 
@@ -366,10 +369,15 @@ class World(object):
                 nw.act_c[s * nw.dim_c:(s + 1) * nw.dim_c, :] = self._as_tensor(value, nw.dim_c).t()
 
     # ---- scenario callbacks: slices of the native observe kernel's outputs ---------------------
-    def _observe_if_stale(self, flags=0):
+    def _observe_if_stale(self):
+        """scenario.observation / reward / benchmark_data called directly (outside env.step): the observe kernel
+        runs into a slab of its OWN, never into the buffers `step` / `reset` hand out (with env.reuse_buffers those
+        alias the caller's tensors).  Per-agent rewards, no shared-reward sum: that is MultiAgentEnv.step's glue."""
         nw = self.bind()
+        if nw.cb_out is None:
+            nw.cb_out = nw.persistent_outputs()
         if not self._obs_valid:
-            nw.observe(flags=0)
+            nw.observe(nw.cb_out, flags=0)
             self._obs_valid = not self.batched  # batched getters hand out writable views
         return nw
 
@@ -381,14 +389,14 @@ class World(object):
 
     def native_observation(self, agent):
         nw = self._observe_if_stale()
-        o = nw.out.obs[self._agent_index(agent)]
+        o = nw.cb_out.obs[self._agent_index(agent)]
         return o if self.batched else self._scalar(o)
 
     def native_reward(self, agent):
         nw = self._observe_if_stale()
-        r = nw.out.rew[self._agent_index(agent)]
+        r = nw.cb_out.rew[self._agent_index(agent)]
         return r if self.batched else float(r[0].item())
 
     def native_benchmark_data(self, agent):
         nw = self._observe_if_stale()
-        return nw.benchmark_data(self._agent_index(agent), self.batched)
+        return nw.benchmark_data(self._agent_index(agent), self.batched, nw.cb_out)

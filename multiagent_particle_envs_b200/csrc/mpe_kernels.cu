@@ -13,6 +13,8 @@
 #include <new>
 #include <utility>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges cost a few ns unless a profiler is attached
+
 #include "mpe_scenarios.cuh"
 #include "mpe_spread_lanes.cuh"
 
@@ -150,7 +152,8 @@ __global__ void __launch_bounds__(kMaxThreads, MPE_MIN_BLOCKS) mpe_kernel(const 
         uintptr_t bits = 0;
 #pragma unroll
         for (int i = 0; i < A; ++i) bits |= reinterpret_cast<uintptr_t>(a.act[i]);
-        bulk = (rows == 32) && ((bits & 15u) == 0);   // warp-uniform
+        // warp-uniform; integer actions (discrete_action_input) are one or two words per world and need no tile
+        bulk = (rows == 32) && ((bits & 15u) == 0) && !(a.flags & MPE_FLAG_DISCRETE_ACTION_INPUT);
         if (bulk && (a.flags & kFlagCpAsync)) {
             // every lane copies 16-byte pieces of the (contiguous) tiles straight into shared memory
             static_for<A>([&](auto ic) {
@@ -202,6 +205,32 @@ __global__ void __launch_bounds__(kMaxThreads, MPE_MIN_BLOCKS) mpe_kernel(const 
     float cact[NC > 0 ? NC : 1];
     // ---- MultiAgentEnv._set_action (environment.py:144-192) --------------------------------
     if constexpr (MODE == kFusedStep || MODE == kSetAction) {
+        if (a.flags & MPE_FLAG_DISCRETE_ACTION_INPUT) {
+            // env.discrete_action_input (environment.py:161-167, 185-187): act_n[i] is int32 [n_env][n_sub_i], one index
+            // per sub-action (movement 0..4, then the utterance 0..dim_c-1); consecutive lanes read consecutive words
+            static_for<A>([&](auto ic) {
+                constexpr int i = decltype(ic)::value;
+                constexpr int NSUB = (P::movable(i) ? 1 : 0) + (i < P::NS ? 1 : 0);
+                const int32_t *row = reinterpret_cast<const int32_t *>(a.act[i]) + wi * NSUB;
+                float x = 0.0f, y = 0.0f;                                       // :145, 162
+                int off = 0;
+                if constexpr (P::movable(i)) {
+                    const int k = row[0];
+                    x = k == 1 ? -1.0f : (k == 2 ? 1.0f : 0.0f);                // :164-165
+                    y = k == 3 ? -1.0f : (k == 4 ? 1.0f : 0.0f);                // :166-167
+                    x = __fmul_rn(x, d.a_sens[i]);                              // :178-181
+                    y = __fmul_rn(y, d.a_sens[i]);
+                    off = 1;
+                }
+                ux[i] = x;
+                uy[i] = y;
+                if constexpr (i < P::NS) {                                      // :186-187 one-hot utterance
+                    const int k = row[off];
+#pragma unroll
+                    for (int q = 0; q < P::DIMC; ++q) cact[i * P::DIMC + q] = (k == q) ? 1.0f : 0.0f;
+                }
+            });
+        } else {
         if (bulk && (a.flags & kFlagCpAsync)) {
             cp_async_wait_all();
             __syncwarp();
@@ -251,6 +280,7 @@ __global__ void __launch_bounds__(kMaxThreads, MPE_MIN_BLOCKS) mpe_kernel(const 
                 for (int q = 0; q < P::DIMC; ++q) cact[i * P::DIMC + q] = row[off + q];
             }
         });
+        }   // float action vectors
         if constexpr (MODE == kSetAction) {
             if (active) {
 #pragma unroll
@@ -290,6 +320,7 @@ __global__ void __launch_bounds__(kMaxThreads, MPE_MIN_BLOCKS) mpe_kernel(const 
     // ---- observation / reward / done / info (environment.py:92-102) -------------------------
     float rew[A];
     float info[(P::INFO > 0 ? P::INFO : 1) * A];
+    P::prepare(d, w);   // per-world predicates shared by all agents' observations (world_comm: forest membership)
     P::reward(d, w, rew, (P::INFO > 0 && a.info != nullptr) ? info : nullptr);
     if (a.flags & MPE_FLAG_SHARED_REWARD) {                                  // :100-102 np.sum(reward_n)
         float s = 0.0f;
@@ -356,9 +387,25 @@ __global__ void __launch_bounds__(128) generic_set_action_kernel(const __grid_co
         if (i >= d.g_agents) break;
         const bool movable = (d.g_movable >> i) & 1u, silent = (d.g_silent >> i) & 1u;
         const int adim = (movable ? 5 : 0) + (silent ? 0 : C);
-        const float *row = a.act[i] + w * adim;
         float x = 0.0f, y = 0.0f;
         int off = 0;
+        if (a.flags & MPE_FLAG_DISCRETE_ACTION_INPUT) {            // environment.py:161-167, 185-187
+            const int nsub = (movable ? 1 : 0) + (silent ? 0 : 1);
+            const int32_t *irow = reinterpret_cast<const int32_t *>(a.act[i]) + w * nsub;
+            if (movable) {
+                const int k = irow[0];
+                x = __fmul_rn(k == 1 ? -1.0f : (k == 2 ? 1.0f : 0.0f), d.a_sens[i]);
+                y = __fmul_rn(k == 3 ? -1.0f : (k == 4 ? 1.0f : 0.0f), d.a_sens[i]);
+                off = 1;
+            }
+            a.u[i * n + w] = make_float2(x, y);
+            if (!silent) {
+                const int k = irow[off];
+                for (int q = 0; q < C; ++q) a.c[(d.g_slot[i] * C + q) * n + w] = (k == q) ? 1.0f : 0.0f;
+            }
+            continue;
+        }
+        const float *row = a.act[i] + w * adim;
         if (movable) {                                             // environment.py:157-181
             float p0 = row[0], p1 = row[1], p2 = row[2], p3 = row[3], p4 = row[4];
             if (a.flags & MPE_FLAG_FORCE_DISCRETE_ACTION) {
@@ -494,6 +541,26 @@ __global__ void __launch_bounds__(256) reset_kernel(const __grid_constant__ Rese
 
 __global__ void bump_epoch_kernel(unsigned long long *epoch) { *epoch += 1ull; }
 
+// ---- diagnostics: a pure streaming kernel with a step's byte counts (bench.py's size-matched ceiling) ------
+// Reads n_read4 float4, then writes n_write4 float4 that depend on what was read (like a step: stores follow the
+// loads), same launch path (programmatic dependent launch) and the same evict-first stores as the step kernel.
+__global__ void __launch_bounds__(256) stream_probe_kernel(const float4 *__restrict__ src, long long n_read4,
+                                                           float4 *__restrict__ dst, long long n_write4) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long nth = static_cast<long long>(gridDim.x) * blockDim.x;
+    float acc = 0.0f;
+#pragma unroll 8
+    for (long long i = tid; i < n_read4; i += nth) {
+        const float4 v = src[i];
+        acc += (v.x + v.y) + (v.z + v.w);
+    }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const float4 o = make_float4(acc, acc, acc, acc);
+#pragma unroll 8
+    for (long long i = tid; i < n_write4; i += nth) __stcs(dst + i, o);
+}
+
 // ---- program table -----------------------------------------------------------------------------
 typedef void (*KernelFn)(StepArgs);
 
@@ -573,6 +640,13 @@ static const Program *programs(int *count) {
 // C ABI
 // =================================================================================================
 using namespace mpe;
+
+namespace {
+struct NvtxRange {   // RAII range around the C-ABI entry points (visible in nsys / ncu --nvtx)
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+}  // namespace
 
 // largest block (in warps) whose warp-private staging fits the 227 KB of dynamic shared memory of an SM
 static int max_warps_per_block(int smem_per_warp) {
@@ -864,7 +938,6 @@ static int fill_actions(mpe_handle h, StepArgs &a, const float *const *act_n) {
 
 extern "C" int mpe_set_action(mpe_handle h, const float *const *act_n, float *u, float *c, uint32_t flags, void *stream) {
     if (!h || !ok8(u)) return MPE_ERR_BAD_ARG;
-    if (flags & MPE_FLAG_DISCRETE_ACTION_INPUT) return MPE_ERR_UNSUPPORTED;
     if (h->prog->NS * h->prog->DIMC > 0 && !ok4(c)) return MPE_ERR_BAD_ARG;
     StepArgs a{};
     int r = fill_actions(h, a, act_n);
@@ -903,7 +976,7 @@ extern "C" int mpe_step(mpe_handle h, void *pv, const void *lm, float *comm, con
                         const float *const *act_n, float *const *obs_n, float *rew, uint8_t *done, float *info,
                         uint32_t flags, void *stream) {
     if (!h) return MPE_ERR_BAD_ARG;
-    if (flags & MPE_FLAG_DISCRETE_ACTION_INPUT) return MPE_ERR_UNSUPPORTED;
+    NvtxRange range("mpe_step");
     StepArgs a{};
     int r = fill_state(h, a, pv, lm, comm, goal);
     if (r) return r;
@@ -948,6 +1021,12 @@ static int step_range(mpe_handle h, void *pv, const void *lm, float *comm, const
     return launch(h, kFusedStep, a, stream, begin, count);
 }
 
+// floats (4-byte words) per world in act_n[i]: the action vector, or one index per sub-action (discrete_action_input)
+static size_t act_row_words(const mpe_env *h, int i, uint32_t flags) {
+    if (flags & MPE_FLAG_DISCRETE_ACTION_INPUT) return (h->desc.agent_movable[i] ? 1 : 0) + (h->desc.agent_silent[i] ? 0 : 1);
+    return static_cast<size_t>(h->prog->act_dim[i]);
+}
+
 static int64_t host_chunk_min() {  // MPE_B200_HOST_CHUNK_MIN: smallest batch that is pipelined (default 262144)
     static const int64_t m = [] { const char *e = getenv("MPE_B200_HOST_CHUNK_MIN"); return e ? atoll(e) : 262144LL; }();
     return m;
@@ -963,7 +1042,7 @@ extern "C" int mpe_step_host(mpe_handle h, void *pv, const void *lm, float *comm
                              float *rew_host, uint8_t *done_host, float *info_host, uint32_t flags, void *stream) {
     if (!h || !act_n_host || !act_n_dev || !obs_n_host || !obs_n_dev || !rew_host || !done_host) return MPE_ERR_BAD_ARG;
     if (h->device < 0) return MPE_ERR_NO_DEVICE;
-    if (flags & MPE_FLAG_DISCRETE_ACTION_INPUT) return MPE_ERR_UNSUPPORTED;
+    NvtxRange range("mpe_step_host");
     const Program *p = h->prog;
     cudaStream_t user = static_cast<cudaStream_t>(stream);
     const size_t n = static_cast<size_t>(h->n);
@@ -984,7 +1063,7 @@ extern "C" int mpe_step_host(mpe_handle h, void *pv, const void *lm, float *comm
         int ns = 0;
         for (int i = 0; i < p->A; ++i)
             seg[ns++] = {reinterpret_cast<char *>(act_n_dev[i]), reinterpret_cast<const char *>(act_n_host[i]),
-                         sizeof(float) * n * p->act_dim[i]};
+                         sizeof(float) * n * act_row_words(h, i, flags)};
         rc = issue_copies(seg, ns, cudaMemcpyHostToDevice, user, "cudaMemcpyAsync(H2D actions)", false);
         if (rc == MPE_OK)
             rc = step_range(h, pv, lm, comm, goal, act_n_dev, obs_n_dev, rew_dev, done_dev, want_info ? info_dev : nullptr,
@@ -1016,8 +1095,8 @@ extern "C" int mpe_step_host(mpe_handle h, void *pv, const void *lm, float *comm
             const int64_t count = (begin + per <= h->n) ? per : h->n - begin;
             cudaStream_t s = h->aux[c & 1];
             for (int i = 0; i < p->A && e == cudaSuccess; ++i)
-                e = cudaMemcpyAsync(act_n_dev[i] + begin * p->act_dim[i], act_n_host[i] + begin * p->act_dim[i],
-                                    sizeof(float) * count * p->act_dim[i], cudaMemcpyHostToDevice, s);
+                e = cudaMemcpyAsync(act_n_dev[i] + begin * act_row_words(h, i, flags), act_n_host[i] + begin * act_row_words(h, i, flags),
+                                    sizeof(float) * count * act_row_words(h, i, flags), cudaMemcpyHostToDevice, s);
             if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemcpyAsync(H2D actions)"); break; }
             rc = step_range(h, pv, lm, comm, goal, act_n_dev, obs_n_dev, rew_dev, done_dev, want_info ? info_dev : nullptr,
                             flags, s, begin, count);
@@ -1049,6 +1128,7 @@ static int reset_impl(mpe_handle h, void *pv, void *lm, float *comm, int32_t *go
                       uint64_t seed, uint64_t world_offset, uint64_t epoch, unsigned long long *epoch_dev, void *stream) {
     if (!h) return MPE_ERR_BAD_ARG;
     if (h->device < 0) return MPE_ERR_NO_DEVICE;
+    NvtxRange range("mpe_reset");
     StepArgs tmp{};
     int r = fill_state(h, tmp, pv, lm, comm, goal);
     if (r) return r;
@@ -1088,6 +1168,31 @@ extern "C" int mpe_reset_dev_epoch(mpe_handle h, void *pv, void *lm, float *comm
                                    uint64_t seed, uint64_t world_offset, unsigned long long *epoch_dev, void *stream) {
     if (!epoch_dev) return MPE_ERR_BAD_ARG;
     return reset_impl(h, pv, lm, comm, goal, mask, seed, world_offset, 0, epoch_dev, stream);
+}
+
+extern "C" int mpe_probe_stream(int device, const void *src, int64_t read_bytes, void *dst, int64_t write_bytes,
+                                int64_t threads, void *stream) {
+    if (!ok16(src) || !ok16(dst) || read_bytes < 0 || write_bytes < 0 || threads < 256) return MPE_ERR_BAD_ARG;
+    int prev = 0;
+    CUDA_TRY(cudaGetDevice(&prev));
+    if (prev != device) CUDA_TRY(cudaSetDevice(device));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>((threads + 255) / 256));
+    cfg.blockDim = dim3(256);
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_mode() ? 1 : 0;
+    const float4 *s4 = static_cast<const float4 *>(src);
+    float4 *d4 = static_cast<float4 *>(dst);
+    long long nr = read_bytes / 16, nw = write_bytes / 16;
+    void *params[] = {&s4, &nr, &d4, &nw};
+    cudaError_t e = cudaLaunchKernelExC(&cfg, reinterpret_cast<const void *>(stream_probe_kernel), params);
+    if (prev != device) cudaSetDevice(prev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelExC(stream_probe)");
+    return MPE_OK;
 }
 
 extern "C" const char *mpe_strerror(int err) {

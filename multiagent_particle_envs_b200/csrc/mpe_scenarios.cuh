@@ -20,6 +20,13 @@ struct WorldRegs {
     float lx[L_], ly[L_];
     float c[NC_ > 0 ? NC_ : 1];  // comm state of the speakers, [speaker][dim_c]
     int g[NG_ > 0 ? NG_ : 1];    // per-world goal indices
+    unsigned aux;                // per-world predicate bits filled by P::prepare (world_comm: forest membership)
+};
+
+// programs without shared per-world predicates inherit the empty prepare()
+struct ProgramBase {
+    template <class W>
+    __device__ __forceinline__ static void prepare(const DevDesc &, W &) {}
 };
 
 // v[idx] for a per-lane index without dynamic register indexing (select chain, N <= 8)
@@ -48,7 +55,7 @@ static bool structure_matches(const mpe_desc &d) {
 // ---------------------------------------------------------------------------------------------
 // simple.py : 1 agent, 1 landmark, nothing collides
 template <int A_, int L_>
-struct Simple {
+struct Simple : ProgramBase {
     static constexpr int A = A_, L = L_, DIMC = 0, NS = 0, INFO = 0, G = 0;
     static constexpr int kScenario = MPE_SCN_SIMPLE;
     using W = WorldRegs<A, L, 0>;
@@ -81,7 +88,7 @@ struct Simple {
 // ---------------------------------------------------------------------------------------------
 // simple_spread.py : N agents, N landmarks, cooperative
 template <int N_>
-struct Spread {
+struct Spread : ProgramBase {
     static constexpr int A = N_, L = N_, DIMC = 2, NS = 0, INFO = 4, G = 0;
     static constexpr int kScenario = MPE_SCN_SPREAD;
     using W = WorldRegs<A, L, 0>;
@@ -156,7 +163,7 @@ struct Spread {
 // ---------------------------------------------------------------------------------------------
 // simple_tag.py : NADV adversaries (first), NGOOD prey, L obstacles
 template <int NADV_, int NGOOD_, int L_>
-struct Tag {
+struct Tag : ProgramBase {
     static constexpr int NADV = NADV_, NGOOD = NGOOD_;
     static constexpr int A = NADV + NGOOD, L = L_, DIMC = 2, NS = 0, INFO = 1, G = 0;
     static constexpr int kScenario = MPE_SCN_TAG;
@@ -229,7 +236,7 @@ struct Tag {
 // simple_world_comm.py : NADV adversaries (agent 0 = leader, the only speaker), NGOOD prey,
 // landmarks = NOBST obstacles ++ NFOOD food ++ 2 forests
 template <int NADV_, int NGOOD_, int NOBST_, int NFOOD_>
-struct WorldComm {
+struct WorldComm : ProgramBase {
     static constexpr int NADV = NADV_, NGOOD = NGOOD_, NOBST = NOBST_, NFOOD = NFOOD_, NFOREST = 2;
     static constexpr int A = NADV + NGOOD, L = NOBST + NFOOD + NFOREST, DIMC = 4, NS = 1, INFO = 1, G = 0;
     static constexpr int FOOD0 = NOBST, FOREST0 = NOBST + NFOOD;
@@ -246,9 +253,21 @@ struct WorldComm {
     __host__ __device__ static constexpr bool landmark_collides(int l) { return l < NOBST; }
     static constexpr bool kSpeedLimit = true;
 
-    __device__ __forceinline__ static bool in_forest(const DevDesc &d, const W &w, int i, int f) {
-        return is_collision(w.px[i], w.py[i], d.a_size[i], w.lx[FOREST0 + f], w.ly[FOREST0 + f],
-                            d.l_size[FOREST0 + f]);                                  // :231-239, 251-252
+    // forest membership of every agent, once per world: bit 2*i + f = is_collision(agent i, forest f)
+    // (:231-239, 251-252).  The reference re-evaluates these 2*A predicates inside every agent's observation
+    // (A*A*2 + 2*A evaluations per world); they only depend on the post-step state, so 2*A suffice.
+    __device__ __forceinline__ static void prepare(const DevDesc &d, W &w) {
+        unsigned bits = 0;
+#pragma unroll
+        for (int i = 0; i < A; ++i)
+#pragma unroll
+            for (int f = 0; f < NFOREST; ++f)
+                if (is_collision(w.px[i], w.py[i], d.a_size[i], w.lx[FOREST0 + f], w.ly[FOREST0 + f], d.l_size[FOREST0 + f]))
+                    bits |= 1u << (2 * i + f);
+        w.aux = bits;
+    }
+    __device__ __forceinline__ static bool in_forest(const DevDesc &, const W &w, int i, int f) {
+        return (w.aux >> (2 * i + f)) & 1u;
     }
 
     template <int I, class Wr>
@@ -346,7 +365,7 @@ struct WorldComm {
 // ---------------------------------------------------------------------------------------------
 // simple_adversary.py : NADV adversaries (first), NGOOD good agents, L landmarks, goal = g[0]
 template <int NADV_, int NGOOD_, int L_>
-struct Adversary {
+struct Adversary : ProgramBase {
     static constexpr int NADV = NADV_, NGOOD = NGOOD_;
     static constexpr int A = NADV + NGOOD, L = L_, DIMC = 2, NS = 0, INFO = L_ + 1, G = 1;
     static constexpr int kScenario = MPE_SCN_ADVERSARY;
@@ -409,7 +428,7 @@ struct Adversary {
 // ---------------------------------------------------------------------------------------------
 // simple_push.py : NADV adversaries (first), NGOOD good agents (all collide), L landmarks, goal = g[0]
 template <int NADV_, int NGOOD_, int L_>
-struct Push {
+struct Push : ProgramBase {
     static constexpr int NADV = NADV_, NGOOD = NGOOD_;
     static constexpr int A = NADV + NGOOD, L = L_, DIMC = 2, NS = 0, INFO = 0, G = 1;
     static constexpr int kScenario = MPE_SCN_PUSH;
@@ -465,7 +484,7 @@ struct Push {
 
 // ---------------------------------------------------------------------------------------------
 // simple_speaker_listener.py : agent 0 = immovable speaker, agent 1 = silent listener, goal = g[0]
-struct SpeakerListener {
+struct SpeakerListener : ProgramBase {
     static constexpr int A = 2, L = 3, DIMC = 3, NS = 1, INFO = 0, G = 1;
     static constexpr int kScenario = MPE_SCN_SPEAKER_LISTENER;
     using W = WorldRegs<A, L, NS * DIMC, G>;
@@ -502,7 +521,7 @@ struct SpeakerListener {
 
 // ---------------------------------------------------------------------------------------------
 // simple_reference.py : 2 agents that move and speak; g[i] = agents[i].goal_b, goal_a = the other agent
-struct Reference {
+struct Reference : ProgramBase {
     static constexpr int A = 2, L = 3, DIMC = 10, NS = 2, INFO = 0, G = 2;
     static constexpr int kScenario = MPE_SCN_REFERENCE;
     using W = WorldRegs<A, L, NS * DIMC, G>;
@@ -539,7 +558,7 @@ struct Reference {
 
 // ---------------------------------------------------------------------------------------------
 // simple_crypto.py : Eve (0, adversary), Bob (1), Alice (2, speaker); nobody moves; g[0] = goal, g[1] = key
-struct Crypto {
+struct Crypto : ProgramBase {
     static constexpr int A = 3, L = 2, DIMC = 4, NS = 3, INFO = 2 * DIMC, G = 2;
     static constexpr int kScenario = MPE_SCN_CRYPTO;
     using W = WorldRegs<A, L, NS * DIMC, G>;

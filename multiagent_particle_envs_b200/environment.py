@@ -49,8 +49,10 @@ class MultiAgentEnv(_Env):
         self.force_discrete_action = world.discrete_action if hasattr(world, 'discrete_action') else False
         self.shared_reward = world.collaborative if hasattr(world, 'collaborative') else False
         self.time = 0
-        #: batched CUDA mode only: write every step into the same output tensors instead of
-        #: returning freshly allocated ones (zero allocations per step; outputs alias across steps)
+        #: batched mode: hand out views of the library's persistent result buffers instead of freshly allocated
+        #: tensors / arrays.  CUDA callers: every step writes the same device slab (results are overwritten by the
+        #: next step).  Host callers: results are views of two flip-flopped pinned slabs (valid until the
+        #: next-but-one step).  Default False = the reference's ownership: every step returns fresh arrays.
         self.reuse_buffers = False
 
         self._custom = (getattr(world, "native_program", None) == "custom")
@@ -107,26 +109,46 @@ class MultiAgentEnv(_Env):
                                       "reference, environment.py:29)")
         return f
 
-    def _onehot_from_indices(self, action_n):
-        """discrete_action_input (environment.py:161-167,185-187): integer sub-actions -> the
-        one-hot vectors the kernel decodes.  Note the reference maps index 1 -> u.x = -1 but
-        one-hot position 1 -> u.x = +1; the permutation below preserves the index semantics."""
+    def _index_tensors(self, action_n, nw):
+        """discrete_action_input (environment.py:161-167,185-187): the kernel decodes integer sub-actions itself
+        (MPE_FLAG_DISCRETE_ACTION_INPUT): action_n[i] becomes int32 [N, n_sub_i] on the device -- a no-op for a
+        contiguous int32 CUDA tensor of that shape; other dtypes / host arrays are converted / uploaded here.
+        Movement index 0 = none, 1 = -x, 2 = +x, 3 = -y, 4 = +y; utterance index k -> one-hot(k)."""
         import torch
-        perm = [0, 2, 1, 4, 3]
-        out = []
         N = self.world.batch_size
-        dev = self.world.bind().device
+        out = []
         for i, a in enumerate(action_n):
-            idx = torch.as_tensor(np.asarray(a) if not torch.is_tensor(a) else a, device=dev).reshape(N, -1).long()
-            parts, col = [], 0
-            for k, size in enumerate(self._sub_sizes[i]):
-                v = idx[:, col]
-                if size == 5 and self.agents[i].movable and k == 0:
-                    v = torch.tensor(perm, device=dev)[v]
-                parts.append(torch.nn.functional.one_hot(v, size).float())
-                col += 1
-            out.append(torch.cat(parts, dim=1).contiguous())
+            nsub = len(self._sub_sizes[i])
+            if not torch.is_tensor(a):
+                a = torch.as_tensor(np.ascontiguousarray(np.asarray(a)).astype(np.int32, copy=False))
+            if a.numel() != N * nsub:
+                raise ValueError("action_n[%d] must hold %d x %d integer sub-actions, got shape %s"
+                                 % (i, N, nsub, tuple(a.shape)))
+            if a.device != nw.device or a.dtype != torch.int32:
+                a = a.to(device=nw.device, dtype=torch.int32)
+            out.append(a.reshape(N, nsub).contiguous())
         return out
+
+    def _step_discrete(self, action_n, nw, flags):
+        world = self.world
+        on_device = all(hasattr(a, "is_cuda") and a.is_cuda for a in action_n)
+        as_numpy = not any(hasattr(a, "dim") for a in action_n)
+        idx = self._index_tensors(action_n, nw)
+        flags |= _lib.FLAG_DISCRETE_ACTION_INPUT
+        if self._custom:
+            return self._step_custom(idx, nw, flags)
+        out = nw.out if (self.reuse_buffers or not world.batched) else nw.new_outputs()
+        nw.step(_lib.ptr_array([t.data_ptr() for t in idx]), out, flags, with_info=self._native_info)
+        self._last_out = out
+        world._obs_valid = False
+        if not world.batched:
+            return self._pack_scalar(nw, out)
+        obs_n, reward_n, done_n, info_n = self._pack_batched(nw, out)
+        if not on_device:     # host callers get host results back
+            obs_n, reward_n, done_n = ([t.cpu() for t in x] for x in (obs_n, reward_n, done_n))
+            if as_numpy:
+                obs_n, reward_n, done_n = ([t.numpy() for t in x] for x in (obs_n, reward_n, done_n))
+        return obs_n, reward_n, done_n, info_n
 
     def step(self, action_n):
         world = self.world
@@ -136,7 +158,7 @@ class MultiAgentEnv(_Env):
             raise ValueError("expected %d actions, got %d" % (self.n, len(action_n)))
         flags = self._flags()
         if self.discrete_action_input:
-            action_n = self._onehot_from_indices(action_n)
+            return self._step_discrete(action_n, nw, flags)
         if self._custom:
             return self._step_custom(action_n, nw, flags)
         if not world.batched and not any(hasattr(a, "dim") for a in action_n):
@@ -182,6 +204,9 @@ class MultiAgentEnv(_Env):
         world = self.world
         acts = []
         for i, a in enumerate(action_n):
+            if flags & _lib.FLAG_DISCRETE_ACTION_INPUT:      # already int32 [N, n_sub] on the device (_index_tensors)
+                acts.append(a)
+                continue
             t = a if torch.is_tensor(a) else torch.as_tensor(np.asarray(a, dtype=np.float32))
             t = t.to(device=nw.device, dtype=torch.float32).reshape(nw.n_env, self._act_dims[i]).contiguous()
             acts.append(t)
@@ -210,7 +235,15 @@ class MultiAgentEnv(_Env):
             raise ValueError("step_async needs a batched env (make_env(..., num_envs=N))")
         if getattr(self, "_pending", None) is not None:
             raise RuntimeError("step_async called twice without step_wait")
+        if self._custom:
+            raise NotImplementedError("step_async is not available for user scenarios (TorchScenario): their "
+                                      "observation / reward callbacks run as torch ops after the native step")
+        if self.discrete_action_input:
+            raise NotImplementedError("step_async takes action vectors; integer actions go through step()")
+        if len(action_n) != self.n:
+            raise ValueError("expected %d actions, got %d" % (self.n, len(action_n)))
         nw = world.bind()
+        self.agents = world.policy_agents
         mode, payload = self._classify(action_n, nw)
         if mode == "cuda":
             raise ValueError("step_async is for host buffers; CUDA-tensor steps are already asynchronous")
@@ -250,6 +283,8 @@ class MultiAgentEnv(_Env):
         if all(torch.is_tensor(a) and a.is_cuda for a in action_n):
             payload = []
             for i, a in enumerate(action_n):
+                if a.device != nw.device:
+                    raise ValueError("action_n[%d] lives on %s but this env's worlds live on %s" % (i, a.device, nw.device))
                 if a.shape != (N, self._act_dims[i]):
                     raise ValueError("action_n[%d] must have shape (%d, %d), got %s" %
                                      (i, N, self._act_dims[i], tuple(a.shape)))
@@ -293,6 +328,12 @@ class MultiAgentEnv(_Env):
         if self.done_callback is not None:
             done_n = [self.done_callback(agent, self.world) for agent in self.agents]
         info_n = {'n': self._info_list(nw, out, True)}
+        if out.slab.device.type == "cpu" and not self.reuse_buffers:
+            # pinned staging slabs are reused every other step: the caller gets its own copies (the reference
+            # returns freshly allocated arrays, and trainers keep them in replay buffers by reference)
+            own = lambda t: t.clone() if hasattr(t, "clone") else t
+            obs_n, reward_n, done_n = [own(o) for o in obs_n], [own(r) for r in reward_n], [own(d) for d in done_n]
+            info_n = {'n': [tuple(own(x) for x in e) if isinstance(e, tuple) else own(e) for e in info_n['n']]}
         if as_numpy:
             obs_n = [o.numpy() for o in obs_n]
             reward_n = [r.numpy() for r in reward_n]

@@ -168,7 +168,8 @@ class NativeWorld(ShapeHandle):
         info_off = off
         off = _align(off + A * self.info_dim * N, 64)
         self._fresh_layout = dict(obs=obs_l, rew=rew_off, info=info_off, words=max(off, 64))
-        self.out = None if self.custom else Outputs(self)   # persistent outputs (observe(), reuse mode)
+        self.out = None if self.custom else Outputs(self)   # persistent outputs (reset / step in reuse mode)
+        self.cb_out = None                 # lazily created: outputs of direct scenario-callback calls (core.py)
         self._host = None                  # lazily created staging for host callers
         self._has_comm = NC > 0
         self._has_goal = self.n_goals > 0
@@ -184,6 +185,9 @@ class NativeWorld(ShapeHandle):
 
     def new_outputs(self):
         return FreshOutputs(self)
+
+    def persistent_outputs(self):
+        return Outputs(self)
 
     # ---- reset -------------------------------------------------------------------------------
     def reset(self, mask=None):

@@ -102,9 +102,23 @@ def import_reference():
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         import multiagent  # noqa: F401  (the reference's)
-        import make_env as ref_make_env
-    assert multiagent.__file__.startswith(REFERENCE_ROOT), multiagent.__file__
-    return ref_make_env.make_env, multiagent
+        try:
+            import make_env as ref_make_env
+            make_env = ref_make_env.make_env
+        except ImportError:
+            # a `pip install --target` of the reference ships the `multiagent` package but not the top-level
+            # make_env.py; this is the body of make_env.py:36-43 expressed through the package's own classes
+            def make_env(scenario_name, benchmark=False):
+                from multiagent.environment import MultiAgentEnv
+                import multiagent.scenarios as scenarios
+                scenario = scenarios.load(scenario_name + ".py").Scenario()
+                world = scenario.make_world()
+                if benchmark:
+                    return MultiAgentEnv(world, scenario.reset_world, scenario.reward, scenario.observation,
+                                         scenario.benchmark_data)
+                return MultiAgentEnv(world, scenario.reset_world, scenario.reward, scenario.observation)
+    assert os.path.realpath(multiagent.__file__).startswith(os.path.realpath(REFERENCE_ROOT)), multiagent.__file__
+    return make_env, multiagent
 
 
 def make_reference_env(name, n=None):

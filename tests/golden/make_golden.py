@@ -22,18 +22,21 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "..", "..", "oracle"))
 import refshim  # noqa: E402
 
+# (scenario, entity-count override, worlds W, recorded steps T): W x T >= 1536 reference steps per scenario
 CONFIGS = [
-    ("simple_adversary", None, 12, 25),
-    ("simple_push", None, 12, 25),
-    ("simple_speaker_listener", None, 12, 25),
-    ("simple_reference", None, 12, 25),
-    ("simple_crypto", None, 12, 25),
-    ("simple", None, 16, 25),
-    ("simple_spread", 3, 16, 25),
-    ("simple_spread", 6, 12, 25),
-    ("simple_tag", None, 16, 25),
-    ("simple_world_comm", None, 12, 25),
+    ("simple_adversary", None, 256, 6),
+    ("simple_push", None, 256, 6),
+    ("simple_speaker_listener", None, 256, 6),
+    ("simple_reference", None, 256, 6),
+    ("simple_crypto", None, 256, 6),
+    ("simple", None, 256, 6),
+    ("simple_spread", 3, 256, 8),
+    ("simple_spread", 6, 256, 6),
+    ("simple_tag", None, 256, 8),
+    ("simple_world_comm", None, 256, 6),
 ]
+PREROLL = 50   # worlds 4..7 (mod 8) first run this many unrecorded reference steps: contact equilibria,
+#                clustered agents pushing against each other, prey pinned against obstacles
 
 
 SEEDS = {"simple": 1, "simple_spread_n3": 2, "simple_spread_n6": 3, "simple_tag": 4, "simple_world_comm": 5,
@@ -115,6 +118,7 @@ def run_config(name, n, W, T, seed, force_discrete=False, discrete_input=False):
             props["act_dims"] = [act_dim(s) for s in env.action_space]
             props["shared_reward"] = int(env.shared_reward)
         mode = w % 4
+        preroll = PREROLL if (w % 8) >= 4 else 0
         if mode == 1:      # squeezed: many contacts
             for e in world.entities:
                 e.state.p_pos = e.state.p_pos * 0.3
@@ -133,7 +137,7 @@ def run_config(name, n, W, T, seed, force_discrete=False, discrete_input=False):
         steps = {k: [] for k in ("act", "pv", "comm", "obs", "rew", "done", "info")}
         temperature = [1.0, 3.0, 0.3, 6.0][mode]
         drift = rng.randn(env.n, 5)
-        for t in range(T):
+        for t in range(-preroll, T):
             acts = []
             for i, sp in enumerate(env.action_space):
                 d = act_dim(sp)
@@ -148,7 +152,11 @@ def run_config(name, n, W, T, seed, force_discrete=False, discrete_input=False):
                     p = np.exp(logits - logits.max())
                     a = np.concatenate([p / p.sum(), rng.uniform(0, 1, d - 5)]) if d > 5 else p / p.sum()
                 acts.append(a)
+            if t == 0 and preroll:      # the recorded trajectory starts from the equilibrated state
+                rec["pv0"][-1], rec["comm0"][-1] = snapshot(world)
             obs_n, rew_n, done_n, info_n = env.step([int(a[0]) for a in acts] if discrete_input else [a.copy() for a in acts])
+            if t < 0:
+                continue
             pv, comm = snapshot(world)
             steps["act"].append(np.concatenate(acts))
             steps["pv"].append(pv)
@@ -184,7 +192,7 @@ def kat():
             a[2 if name == "simple" else min(i + 1, 4)] = 1.0
             acts.append(a)
         for _ in range(2):
-            obs_n, rew_n, done_n, info_n = env.step([int(a[0]) for a in acts] if discrete_input else [a.copy() for a in acts])
+            obs_n, rew_n, done_n, info_n = env.step([a.copy() for a in acts])
         pv, comm = snapshot(env.world)
         out[name + "/pv0"], out[name + "/lm"], out[name + "/comm0"] = pv0, lm, comm0
         out[name + "/act"] = np.concatenate(acts)
@@ -206,12 +214,12 @@ def main():
         print(tag, {k: v.shape for k, v in data.items() if not k.startswith("prop_")})
     if only:
         return
-    data = run_config("simple_tag", None, 8, 10, seed=77, force_discrete=True)
+    data = run_config("simple_tag", None, 64, 8, seed=77, force_discrete=True)
     np.savez_compressed(os.path.join(HERE, "simple_tag_force_discrete.npz"), **data)
-    data = run_config("simple_tag", None, 8, 10, seed=78, discrete_input=True)
+    data = run_config("simple_tag", None, 64, 8, seed=78, discrete_input=True)
     np.savez_compressed(os.path.join(HERE, "simple_tag_discrete_input.npz"), **data)
     for counts, tag in (((1, 1, 2), "simple_tag_1v1"), ((4, 2, 2), "simple_tag_4v2"), ((6, 2, 3), "simple_tag_6v2")):
-        data = run_config("simple_tag", counts, 6, 10, seed=80 + counts[0])     # entity-count variants
+        data = run_config("simple_tag", counts, 64, 6, seed=80 + counts[0])     # entity-count variants
         np.savez_compressed(os.path.join(HERE, tag + ".npz"), **data)
     np.savez_compressed(os.path.join(HERE, "kat.npz"), **kat())
 

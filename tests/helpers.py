@@ -107,3 +107,63 @@ def split_cols(a, dims):
         out.append(a[..., c:c + d])
         c += d
     return out
+
+
+# ---- accounting for contact-indicator mismatches between fp32 and fp64 ---------------------------------
+# Rewards / benchmark_data contain indicator terms ([dist < size_a + size_b], [min dist < 0.1]).  An fp32
+# evaluation may legitimately flip one when the fp64 distance sits within rounding of its threshold.  Every
+# mismatch must be explained that way: (1) the difference is an integer multiple of the scenario's contact
+# quantum and (2) some entity pair of that world is within `margin` of a threshold in the fp64 reference state.
+CONTACT_QUANTUM = {"simple_spread": 1.0, "simple_tag": 10.0, "simple_world_comm": 1.0}   # world_comm: 5a + 2b
+INFO_QUANTUM = 1.0                                                                       # counts
+
+
+def scenario_of(tag):
+    for name in ("simple_spread", "simple_tag", "simple_world_comm"):
+        if tag.startswith(name):
+            return name
+    return tag
+
+
+def threshold_margin(scn, pv_post, lm, a_size, l_size):
+    """per world: min over entity pairs of |dist - threshold| in the given (fp64) post-step state"""
+    p = np.asarray(pv_post, dtype=np.float64)[:, :, 0:2]
+    lm = np.asarray(lm, dtype=np.float64)
+    n, A = p.shape[:2]
+    best = np.full(n, np.inf)
+    for i in range(A):
+        for j in range(i + 1, A):
+            d = np.sqrt(((p[:, i] - p[:, j]) ** 2).sum(-1))
+            best = np.minimum(best, np.abs(d - (a_size[i] + a_size[j])))
+        for l in range(lm.shape[1]):
+            d = np.sqrt(((p[:, i] - lm[:, l]) ** 2).sum(-1))
+            best = np.minimum(best, np.abs(d - (a_size[i] + l_size[l])))
+            if scn == "simple_spread":
+                best = np.minimum(best, np.abs(d - 0.1))      # occupied_landmarks (simple_spread.py:56-57)
+    return best
+
+
+def explain_flag_mismatches(tag, rew, ref_rew, info, ref_info, pv_post64, lm64, a_size, l_size,
+                            rtol=1e-5, atol=5e-6, margin=2e-6):
+    """assert that every reward / info mismatch is a flipped contact indicator; returns #worlds with one"""
+    scn = scenario_of(tag)
+    ok = np.isclose(rew, ref_rew, rtol=rtol, atol=atol)
+    bad = ~ok.all(axis=1)
+    oki = None
+    if info is not None and info.size:
+        oki = np.isclose(info, ref_info, rtol=rtol, atol=atol)
+        bad |= ~oki.reshape(oki.shape[0], -1).all(axis=1)
+    if not bad.any():
+        return 0
+    q = CONTACT_QUANTUM.get(scn)
+    assert q is not None, "%s has no contact indicators: reward mismatch in worlds %s" % (tag, np.where(bad)[0][:8])
+    m = threshold_margin(scn, pv_post64, lm64, a_size, l_size)
+    assert (m[bad] < margin).all(), "unexplained mismatch: worlds %s have no pair within %g of a threshold (margins %s)" % (
+        np.where(bad)[0][:8], margin, m[bad][:8])
+    d = (np.asarray(rew, np.float64) - ref_rew)[~ok] / q
+    assert (np.abs(d - np.round(d)) < 1e-3).all() and (np.round(d) != 0).all(), "reward difference is not a multiple of %g: %s" % (q, d[:8])
+    if oki is not None:
+        di = (np.asarray(info, np.float64) - ref_info)[~oki]
+        # counts differ by integers; simple_spread's info[0] is the reward itself (quantum 1 as well)
+        assert (np.abs(di - np.round(di)) < 1e-3).all(), di[:8]
+    return int(bad.sum())

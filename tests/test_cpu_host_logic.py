@@ -262,8 +262,29 @@ def test_bench_reference_arm_contract():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == r["value"] and "np_port" in cb["sample"]
     assert r["e2e"] == {"value": r["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert r["config"]["workload"].startswith("simple_spread N=3") and r["config"]["n_env_per_gpu"] == 65536
+    # the CPU sample is decoupled from --steps: 60 bench steps x 100 calls = 6000 env.step calls per process
+    assert r["steps_timed_per_process"] == 6000 and cb["warmup_per_process"] >= 100
+    # the arm never loads CUDA or the product library: only the CPU oracle (its own infrastructure)
+    assert r["native_so_in_process"] == ["oracle/_build/libmpe_oracle.so"], r["native_so_in_process"]
+    # same config dict as the GPU arm builds for this workload (ring sized on input bytes: 132 B x 65536 x 31 > 2 x L2)
+    assert r["config"]["ring_batches"] == 31 and r["config"]["bytes_per_env_step"] == 411
     # under torchrun every rank but 0 exits silently
     env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
                           "--steps", "10", "--warmup", "3"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+@pytest.mark.parametrize("tag", list(CONFIGS))
+def test_bench_shape_formula_equals_library(tag):
+    """bench.py's CPU arm computes the workload description without dlopening libmpe_b200.so; its restatement of
+    mpe_bytes_per_env_step (and of the input bytes the ring is sized on) must equal what the library reports"""
+    sys.path.insert(0, ROOT)
+    import bench
+    name, kw = CONFIGS[tag]
+    w = bench.scenario_world(name, kw)
+    act, obs, bpe, ibpe = bench.shapes_from_oracle(w.descriptor())
+    sh = w.native_shapes()
+    assert act == sh.act_dims and obs == sh.obs_dims and bpe == sh.bytes_per_env_step
+    assert 0 < ibpe < bpe and bench.ring_size(ibpe, 65536) * ibpe * 65536 > 2 * bench.L2_BYTES
+    assert bench.ring_size(ibpe, 1 << 22) == 3

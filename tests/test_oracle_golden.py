@@ -7,7 +7,7 @@ tolerance (rtol 1e-5, atol 1e-6 per step)."""
 import numpy as np
 import pytest
 
-from helpers import CONFIGS, descriptor, load_golden, step_flags
+from helpers import CONFIGS, descriptor, explain_flag_mismatches, load_golden, step_flags
 from oracle import Oracle
 
 TAGS = list(CONFIGS)
@@ -49,6 +49,7 @@ def test_oracle_f32_single_step_within_tolerance(tag):
     orc = Oracle(descriptor(tag), "f32")
     flags = step_flags(g)
     W, T = g["act"].shape[:2]
+    flipped = 0
     for t in range(T):
         pv_in = g["pv0"] if t == 0 else g["pv"][:, t - 1]
         comm_in = g["comm0"] if t == 0 else g["comm"][:, t - 1]
@@ -56,10 +57,12 @@ def test_oracle_f32_single_step_within_tolerance(tag):
         np.testing.assert_allclose(pv, g["pv"][:, t], rtol=1e-5, atol=1e-6)
         np.testing.assert_allclose(obs, g["obs"][:, t], rtol=1e-5, atol=1e-6)
         assert np.array_equal(done, g["done"][:, t])
-        # rewards contain contact indicators: compare where the fp64 reference is not within
-        # 1e-6 of a contact threshold (checked through the reward value itself)
-        close = np.isclose(rew, g["rew"][:, t], rtol=1e-5, atol=2e-6)
-        assert close.mean() > 0.99, close.mean()
+        # rewards / benchmark_data contain contact indicators: every mismatch must be a flipped indicator whose
+        # fp64 distance is within 2e-6 of its threshold (helpers.explain_flag_mismatches)
+        flipped += explain_flag_mismatches(tag, rew, g["rew"][:, t], info if orc.info_dim else None,
+                                           g["info"][:, t] if orc.info_dim else None, g["pv"][:, t], g["lm"],
+                                           g["prop_agent_size"], g["prop_landmark_size"], atol=2e-6)
+    assert flipped <= max(2, W * T // 200), flipped      # and they are rare
 
 
 def test_known_answers_of_survey():

@@ -1,7 +1,14 @@
 #!/usr/bin/env python
-"""Batch-size sweep of the fused step kernel (device-resident, CUDA-graph replay over a ring of batches
-whose working set exceeds 2x L2): env-steps/s and achieved fraction of the measured HBM roofline for the
-BASELINE.json scenarios at 1k..1M worlds.  Writes JSON lines (one per point) to stdout / --out."""
+"""Batch-size sweep of the fused step (BASELINE north star: simple_spread N=3 and simple_tag at 1k..1M worlds on
+1 / 2 / 4 / 8 B200): device-resident, strictly serialized launches replayed from CUDA graphs over bench.py's ring
+(inputs > 2x L2), env-steps/s and achieved fraction of the measured HBM roofline per point.
+
+    python tools/sweep.py --out profiles/r2_sweep_n1.jsonl                                   # one GPU
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \\
+        --master-port 29511 tools/sweep.py --out profiles/r2_sweep_n8.jsonl                    # --num-envs is per GPU
+
+Under torchrun every rank sweeps its own shard (weak scaling); per point the ranks exchange one all-gather of
+(env_steps, seconds) and rank 0 writes whole-job throughput with time = max over ranks."""
 import argparse
 import json
 import os
@@ -23,76 +30,67 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scenarios", default="simple_spread,simple_tag,simple_spread_n6,simple_world_comm")
     ap.add_argument("--sizes", default="1024,4096,16384,65536,262144,1048576")
-    ap.add_argument("--seconds", type=float, default=0.25)
+    ap.add_argument("--seconds", type=float, default=0.2)
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
+    rank, local_rank, world = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("LOCAL_RANK", 0), ("WORLD_SIZE", 1)))
+    import bench
+    bench.pin_to_gpu_numa(local_rank)
     import torch
+    import torch.distributed as dist
     import __graft_entry__ as g
     g.build(quiet=True)
-    from multiagent_particle_envs_b200 import _lib, make_env
-    from bench import measured_peak
-    peak, src = measured_peak()
-    dev = torch.device("cuda", 0)
-    out = open(args.out, "w") if args.out else None
+    from multiagent_particle_envs_b200.sharding import aggregate_counters
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peak, src = bench.measured_peak()
+    out = open(args.out, "w") if (args.out and rank == 0) else None
+    spin = int(200e-6 * getattr(torch.cuda.get_device_properties(dev), "clock_rate", 1.9e6) * 1e3)
     for sc in args.scenarios.split(","):
+        spec = SCENARIOS.get(sc, dict(name=sc, kw={}))
         for n in [int(x) for x in args.sizes.split(",")]:
-            spec = SCENARIOS.get(sc, dict(name=sc, kw={}))
-            probe = make_env(spec["name"], num_envs=n, device=dev, **spec["kw"])
-            bpe = probe.world.native_shapes().bytes_per_env_step
-            ring_n = max(2, min(64, int(2.2 * 126 * 2**20 / (bpe * n)) + 1))
-            ring = []
-            for b in range(ring_n):
-                env = make_env(spec["name"], num_envs=n, device=dev, seed=b, **spec["kw"])
-                env.reset()
-                nw = env.world.native
-                gen = torch.Generator(device=dev).manual_seed(b)
-                acts = []
-                for d in nw.act_dims:
-                    p = torch.softmax(torch.randn(n, 5, device=dev, generator=gen), 1)
-                    if d > 5:
-                        p = torch.cat([p, torch.rand(n, d - 5, device=dev, generator=gen)], 1)
-                    acts.append(p.contiguous())
-                ring.append((env, nw, acts, _lib.ptr_array([t.data_ptr() for t in acts]), env._flags()))
-            stream = torch.cuda.Stream(dev)
-            with torch.cuda.stream(stream):
-                for env, nw, acts, ptrs, flags in ring:
-                    nw.step(ptrs, nw.out, flags)
-                stream.synchronize()
-                graph = torch.cuda.CUDAGraph()
-                reps_in_graph = max(1, 64 // ring_n)
-                with torch.cuda.graph(graph, stream=stream):
-                    for _ in range(reps_in_graph):
-                        for env, nw, acts, ptrs, flags in ring:
-                            nw.step(ptrs, nw.out, flags)
-                steps_per_replay = reps_in_graph * ring_n
+            ring = bench.Ring(spec["name"], spec["kw"], n, dev, rank, world)
+            k = ring.R * max(1, 64 // ring.R)                 # whole ring passes, 64+ launches per graph
+            plan = ring.plan(k)
+            with torch.cuda.stream(ring.stream):
                 for _ in range(3):
-                    graph.replay()
-                stream.synchronize()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(stream)
-                graph.replay()
-                e1.record(stream)
-                stream.synchronize()
-                est = e0.elapsed_time(e1) / 1e3
-                replays = max(3, int(args.seconds / max(est, 1e-6)))
-                e0.record(stream)
-                for _ in range(replays):
-                    graph.replay()
-                e1.record(stream)
-                stream.synchronize()
-                sec = e0.elapsed_time(e1) / 1e3
-            steps = replays * steps_per_replay
-            us = 1e6 * sec / steps
-            gbs = bpe * n / (sec / steps) / 1e9
-            rec = {"scenario": sc, "n_env": n, "ring": ring_n, "us_per_step": us, "env_steps_per_sec": n * steps / sec,
-                   "bytes_per_env_step": bpe, "achieved_gbs": gbs, "peak_gbs": peak, "frac": gbs / peak, "peak_source": src}
-            line = json.dumps(rec)
-            print(line, flush=True)
-            if out:
-                out.write(line + "\n")
-                out.flush()
-            del ring, graph
+                    ring.run(plan)
+                ring.stream.synchronize()
+            est = ring.timed(plan, spin)
+            reps = max(3, int(args.seconds / max(est, 1e-6)))
+            if world > 1:
+                t = torch.tensor([reps], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                reps = int(t.item())
+                dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(ring.stream):
+                torch.cuda._sleep(spin)
+                e0.record(ring.stream)
+                for _ in range(reps):
+                    ring.run(plan)
+                e1.record(ring.stream)
+                ring.stream.synchronize()
+            sec = e0.elapsed_time(e1) / 1e3
+            steps = reps * k
+            total, mx, _ = aggregate_counters(n * steps, sec)
+            if rank == 0:
+                per_gpu_gbs = ring.bytes_per_env * n / (mx / steps) / 1e9
+                rec = {"scenario": sc, "n_gpus": world, "n_env_per_gpu": n, "ring": ring.R, "steps": steps,
+                       "us_per_step": 1e6 * mx / steps, "env_steps_per_sec": total / mx,
+                       "bytes_per_env_step": ring.bytes_per_env, "achieved_gbs_per_gpu": per_gpu_gbs, "peak_gbs": peak,
+                       "frac": per_gpu_gbs / peak, "peak_source": src}
+                line = json.dumps(rec)
+                print(line, flush=True)
+                if out:
+                    out.write(line + "\n")
+                    out.flush()
+            del ring, plan
             torch.cuda.empty_cache()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
