@@ -81,9 +81,12 @@ def shapes_from_oracle(desc):
     return list(o.act_dims), list(o.obs_dims), 4 * floats + A, 4 * in_floats
 
 
-def ring_size(input_bytes_per_env, n_env, requested=0):
+MAX_RING = 256      # tiny batches (< ~8k worlds) would need thousands of ring slots; they are launch-bound anyway
+
+
+def ring_size(input_bytes_per_env, n_env, requested=0, cap=MAX_RING):
     need = int(2 * L2_BYTES / (input_bytes_per_env * n_env)) + 1
-    return max(3, need, requested or 0)
+    return max(3, min(need, cap), requested or 0)
 
 
 def workload_config(scenario, kw, n_env, n_agents, bytes_per_env, input_bytes_per_env, n_gpus, ring):
@@ -94,8 +97,9 @@ def workload_config(scenario, kw, n_env, n_agents, bytes_per_env, input_bytes_pe
             "agents": n_agents, "episode_length": EPISODE, "ring_batches": ring,
             "bytes_per_env_step": bytes_per_env, "input_bytes_per_env_step": input_bytes_per_env,
             "l2_policy": "inputs larger than L2: steps rotate over %d independent batches; their INPUTS alone (state + "
-                         "actions, %.1f MB per batch) total %.0f MB > 2 x 126 MB L2, all bytes %.0f MB"
+                         "actions, %.1f MB per batch) total %.0f MB %s 2 x 126 MB L2, all bytes %.0f MB"
                          % (ring, input_bytes_per_env * n_env / 1e6, ring * input_bytes_per_env * n_env / 1e6,
+                            ">" if ring * input_bytes_per_env * n_env > 2 * L2_BYTES else "(ring capped) <",
                             ring * bytes_per_env * n_env / 1e6),
             "actions": "softmax of N(0,1) logits (+ uniform utterances), pre-generated per batch, resident in HBM",
             "parallelism": "dp%d (independent shards, no data-path collective)" % n_gpus}
@@ -401,7 +405,7 @@ def pin_to_gpu_numa(local_rank):
 class Ring(object):
     """R independent env batches with resident actions and outputs + the CUDA-graph plans that step them"""
 
-    def __init__(self, scenario, kw, n_env, dev, rank, world, requested_ring=0):
+    def __init__(self, scenario, kw, n_env, dev, rank, world, requested_ring=0, max_ring=MAX_RING):
         import torch
         from multiagent_particle_envs_b200 import _lib, make_env
         self.torch, self.dev, self.n_env = torch, dev, n_env
@@ -413,7 +417,7 @@ class Ring(object):
         A, L = sh.n_agents, sh.n_landmarks
         unread = {_lib.SCN_CRYPTO: 4 * A + 2 * L, _lib.SCN_SPEAKER_LISTENER: 4}.get(int(sh.desc.scenario), 0)
         self.input_bytes_per_env = 4 * (4 * A + 2 * L + sh.n_goals - unread + sum(sh.act_dims))
-        self.R = ring_size(self.input_bytes_per_env, n_env, requested_ring)
+        self.R = ring_size(self.input_bytes_per_env, n_env, requested_ring, max_ring)
         self.bytes_per_step = self.bytes_per_env * n_env
         self.slots = []
         for b in range(self.R):

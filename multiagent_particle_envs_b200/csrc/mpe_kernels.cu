@@ -118,14 +118,32 @@ __device__ __forceinline__ void physics(const DevDesc &d, typename P::W &w, cons
 #define MPE_MIN_BLOCKS 1   // 512-thread bound x 1 block = the same 128-register budget that measured best
 #endif
 
-template <class P, int MODE>
+// bar.sync among the 64 threads of a warp pair; the float operands make the barrier wait for the loads that
+// produced them (one component per LDG.128 suffices: the four components of a float4 arrive together)
+template <int N>
+__device__ __forceinline__ void pair_barrier(int id, const float (&v)[N]) {
+    static_assert(N <= 8, "at most 8 agents");
+    asm volatile("bar.sync %0, 64;" ::"r"(id), "f"(v[0]), "f"(v[N > 1 ? 1 : 0]), "f"(v[N > 2 ? 2 : 0]), "f"(v[N > 3 ? 3 : 0]),
+                 "f"(v[N > 4 ? 4 : 0]), "f"(v[N > 5 ? 5 : 0]), "f"(v[N > 6 ? 6 : 0]), "f"(v[N > 7 ? 7 : 0]) : "memory");
+}
+
+// SPLIT (fused step only): TWO warps share a 32-world tile.  Both load the state and the actions and run the physics
+// (bit-identical results); warp 2k writes the new state and the observations of the even agents, warp 2k+1 the rewards /
+// dones / info and the observations of the odd agents.  It doubles the warps in flight for the same batch: batches too
+// small to fill the machine with one lane per world (world_comm at 32 768 worlds = 1.7 warps per scheduler, ~3000
+// dependent instructions each) are bound by instruction latency, not by HBM, and the observation half is most of it.
+template <class P, int MODE, bool SPLIT = false>
 __global__ void __launch_bounds__(kMaxThreads, MPE_MIN_BLOCKS) mpe_kernel(const __grid_constant__ StepArgs a) {
+    static_assert(!SPLIT || MODE == kFusedStep, "warp pairs exist for the fused step only");
     constexpr int A = P::A, L = P::L, NC = Shape<P>::kNC;
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int half = SPLIT ? (warp & 1) : 0;
     const int64_t n = a.n;
     const int64_t end = a.begin + a.count;
-    const int64_t w0 = a.begin + (static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + warp) * 32;
+    const int64_t tile = SPLIT ? static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 6) + (warp >> 1)
+                               : static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + warp;
+    const int64_t w0 = a.begin + tile * 32;
     // Programmatic dependent launch (MPE_B200_PDL, see launch()): the index arithmetic and the first touches of the
     // parameter block (constant-bank misses) run before the wait; no global memory is touched before the previous
     // grid has completed and flushed.  A warp that exits early counts as having released the dependent grid.
@@ -304,10 +322,12 @@ __global__ void __launch_bounds__(kMaxThreads, MPE_MIN_BLOCKS) mpe_kernel(const 
     if (a.flags & kFlagPdlAfterLoads) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // ---- World.step (core.py:117-131) --------------------------------------------------------
     if constexpr (MODE == kFusedStep || MODE == kWorldStep) {
+        // the partner warp must have received the old state before this warp overwrites it in place
+        if constexpr (SPLIT) pair_barrier(1 + (warp >> 1), w.px);
         physics<P>(d, w, ux, uy);
 #pragma unroll
         for (int q = 0; q < NC; ++q) w.c[q] = cact[q];  // update_agent_state (core.py:171-177)
-        if (active) {
+        if (active && half == 0) {
 #pragma unroll
             for (int i = 0; i < A; ++i)
                 if (P::movable(i)) a.pv[i * n + wi] = make_float4(w.px[i], w.py[i], w.vx[i], w.vy[i]);
@@ -338,6 +358,7 @@ __global__ void __launch_bounds__(kMaxThreads, MPE_MIN_BLOCKS) mpe_kernel(const 
         static_for<A>([&](auto ic) {
             constexpr int i = decltype(ic)::value;
             constexpr int OD = P::obs_dim(i);
+            if (SPLIT && (i & 1) != half) return;     // warp-uniform: the partner warp writes this agent
             TileWriter<OD> o(s_warp + Shape<P>::obs_off(i), lane);
             P::template observe<i>(d, w, o);
             if constexpr (!Shape<P>::obs_dense(i)) {  // padded tiles share one slot
@@ -350,16 +371,18 @@ __global__ void __launch_bounds__(kMaxThreads, MPE_MIN_BLOCKS) mpe_kernel(const 
         static_for<A>([&](auto ic) {
             constexpr int i = decltype(ic)::value;
             constexpr int OD = P::obs_dim(i);
+            if (SPLIT && (i & 1) != half) return;
             if constexpr (Shape<P>::obs_dense(i)) obs_tile_store<OD>(a.obs[i] + w0 * OD, s_warp + Shape<P>::obs_off(i), lane);
         });
     } else if (active) {  // the batch's last, partial warp: rows go straight to global memory
         static_for<A>([&](auto ic) {
             constexpr int i = decltype(ic)::value;
+            if (SPLIT && (i & 1) != half) return;
             RowWriter o{a.obs[i] + wi * P::obs_dim(i)};
             P::template observe<i>(d, w, o);
         });
     }
-    if (active) {
+    if (active && (!SPLIT || half == 1)) {
 #pragma unroll
         for (int i = 0; i < A; ++i) {
             a.rew[i * n + wi] = rew[i];
@@ -569,6 +592,7 @@ struct Program {
     bool (*validate)(const mpe_desc &);
     KernelFn fn[4];
     int smem_bytes;  // dynamic shared memory per WARP
+    KernelFn split_fn;  // fused step with a warp PAIR per 32-world tile (small batches of heavy scenarios)
     KernelFn lanes_fn;  // lane-per-agent fused step (simple_spread only), else null
     int lanes_smem, lanes_wpw;
     int A, L, NS, DIMC, INFO, G;
@@ -585,6 +609,7 @@ static Program make_program() {
     p.fn[kSetAction] = mpe_kernel<P, kSetAction>;
     p.fn[kWorldStep] = mpe_kernel<P, kWorldStep>;
     p.fn[kObserve] = mpe_kernel<P, kObserve>;
+    p.split_fn = P::A >= 2 ? mpe_kernel<P, kFusedStep, true> : nullptr;
     p.smem_bytes = Shape<P>::kWarpBytes;  // per warp
     p.A = P::A; p.L = P::L; p.NS = P::NS; p.DIMC = P::DIMC; p.INFO = P::INFO; p.G = P::G;
     for (int i = 0; i < P::A; ++i) { p.obs_dim[i] = P::obs_dim(i); p.act_dim[i] = P::act_dim(i); }
@@ -713,6 +738,9 @@ extern "C" int mpe_create(const mpe_desc *desc, int64_t n_env, int device, mpe_h
                                               prog->smem_bytes * max_warps_per_block(prog->smem_bytes)));
         if (prog->lanes_fn)
             CUDA_TRY(cudaFuncSetAttribute(prog->lanes_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, prog->lanes_smem * 4));
+        if (prog->split_fn && prog->smem_bytes > 0)
+            CUDA_TRY(cudaFuncSetAttribute(prog->split_fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          prog->smem_bytes * max_warps_per_block(prog->smem_bytes)));
         CUDA_TRY(cudaSetDevice(prev));
     }
 
@@ -858,13 +886,22 @@ static int launch(mpe_handle h, int mode, StepArgs &args, void *stream, int64_t 
         __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED);
         return MPE_OK;
     }
-    const int64_t warps = (args.count + 31) / 32;
+    int64_t warps = (args.count + 31) / 32;
+    // Warp pairs (see mpe_kernel<..., SPLIT>): MPE_B200_SPLIT = 0 never, 1 always, unset: when one warp per tile leaves
+    // the machine under ~2.5 warps per scheduler AND the scenario is heavy enough (>= 4 agents) for instruction
+    // latency rather than HBM to bound the step -- thresholds from measurements, see profiles/
+    static const int split_env = [] { const char *e = getenv("MPE_B200_SPLIT"); return e ? atoi(e) : -1; }();
+    static const int64_t split_max_warps = [] { const char *e = getenv("MPE_B200_SPLIT_MAX_WARPS"); return e ? atoll(e) : 148LL * 10; }();
+    const bool split = mode == kFusedStep && h->prog->split_fn != nullptr &&
+                       (split_env == 1 || (split_env < 0 && h->prog->A >= 4 && warps <= split_max_warps));
+    if (split) warps *= 2;
     // Warps are autonomous, so the block size only sets scheduling granularity (measured at 65536 worlds:
     // 1 / 2 / 4 warps per block = 6.69 / 6.34 / 7.06 us per step): tiny batches use one warp per block so
     // that the few blocks spread over all 148 SMs, mid-size batches two, large ones four.
     static const int wpb_env = [] { const char *e = getenv("MPE_B200_WPB"); int v = e ? atoi(e) : 0; return (v >= 1 && v <= kMaxWarpsPerBlock) ? v : 0; }();
     int wpb = wpb_env ? wpb_env : (warps <= 148 * 4 ? 1 : (warps <= 148 * 64 ? 2 : 4));
     if (wpb > max_warps_per_block(h->prog->smem_bytes)) wpb = max_warps_per_block(h->prog->smem_bytes);
+    if (split) wpb = (wpb < 2) ? 2 : (wpb & ~1);      // a pair lives in one block
     const int64_t blocks = (warps + wpb - 1) / wpb;
     if (blocks > 0x7fffffffLL) return MPE_ERR_BAD_ARG;
     int prev = 0;
@@ -889,7 +926,7 @@ static int launch(mpe_handle h, int mode, StepArgs &args, void *stream, int64_t 
     static const bool cpasync = [] { const char *e = getenv("MPE_B200_ACT_STAGING"); return !(e && e[0] == 't'); }();
     if (cpasync) args.flags |= kFlagCpAsync;
     void *params[] = {&args};
-    cudaError_t e = cudaLaunchKernelExC(&cfg, reinterpret_cast<const void *>(h->prog->fn[mode]), params);
+    cudaError_t e = cudaLaunchKernelExC(&cfg, reinterpret_cast<const void *>(split ? h->prog->split_fn : h->prog->fn[mode]), params);
     if (prev != h->device) cudaSetDevice(prev);
     if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelExC");
     __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED);

@@ -343,3 +343,52 @@ def test_step_async_matches_step_and_interleaves_two_envs():
                 assert isinstance(x, np.ndarray) and np.array_equal(x, y)
     with pytest.raises(RuntimeError):
         envs[0].step_wait()
+
+
+_SPLIT_SCRIPT = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(root)r + "/tests")
+from helpers import make_product_env
+out = {}
+for tag, n in (("simple_spread_n3", 5003), ("simple_spread_n6", 2049), ("simple_tag", 4097), ("simple_world_comm", 3001),
+               ("simple_reference", 1000), ("simple_crypto", 999), ("simple_speaker_listener", 64), ("simple_push", 33)):
+    env = make_product_env(tag, num_envs=n, seed=21)
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(4)
+    nw = env.world.native
+    for t in range(3):
+        acts = []
+        for d, ag in zip(nw.act_dims, env.agents):
+            parts = [torch.softmax(3 * torch.randn(n, 5, device="cuda", generator=g), 1)] if ag.movable else []
+            if d - (5 if ag.movable else 0) > 0:
+                parts.append(torch.rand(n, d - (5 if ag.movable else 0), device="cuda", generator=g))
+            acts.append(torch.cat(parts, 1).contiguous())
+        obs_n, rew_n, done_n, _ = env.step(acts)
+    out[tag + "_obs"] = torch.cat(obs_n, 1).cpu().numpy()
+    out[tag + "_rew"] = torch.stack(rew_n).cpu().numpy()
+    out[tag + "_done"] = torch.stack(done_n).cpu().numpy()
+    out[tag + "_pv"] = nw.agent_pv.cpu().numpy()
+    out[tag + "_comm"] = nw.comm.cpu().numpy()
+    if env._last_out.info is not None:
+        out[tag + "_info"] = env._last_out.info.cpu().numpy()
+np.savez(sys.argv[1], **out)
+"""
+
+
+def test_warp_pair_split_kernel_is_bit_identical(tmp_path):
+    """MPE_B200_SPLIT=1 runs every fused step with a warp PAIR per 32-world tile (both warps do the physics, each
+    writes half of the outputs; the in-place state update is ordered by a pair barrier).  Three consecutive steps
+    of eight scenarios with ragged batch sizes must equal the one-warp-per-tile kernel bit for bit."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for mode in ("0", "1"):
+        path = str(tmp_path / ("split%s.npz" % mode))
+        env = dict(os.environ, MPE_B200_SPLIT=mode)
+        subprocess.run([sys.executable, "-c", _SPLIT_SCRIPT % {"root": root}, path], check=True, env=env, timeout=900)
+        res[mode] = dict(np.load(path))
+    assert set(res["0"]) == set(res["1"]) and len(res["0"]) >= 40
+    for k in res["0"]:
+        assert np.array_equal(res["0"][k], res["1"][k]), k

@@ -57,12 +57,13 @@ def main():
     rows = []
     for mangled, (reg, stack) in usage.items():
         nm = names[mangled]
-        m = re.match(r"void mpe::mpe_kernel<mpe::(.+), 0>\(", nm)
+        m = re.match(r"void mpe::mpe_kernel<mpe::(.+), 0, (false|true)>\(", nm)
         if not m:
             continue
+        label = m.group(1) + (" (warp pair)" if m.group(2) == "true" else "")
         c = mix.get(mangled, {})
         fp = sum(c[k] for k in ("FADD", "FMUL", "FFMA", "FSETP", "FSEL", "FMNMX", "FMNMX3"))
-        rows.append((m.group(1), reg, stack, c["total"], fp, c["MUFU"], c["LDG"], c["LDGSTS"], c["LDS"], c["STS"], c["STG"],
+        rows.append((label, reg, stack, c["total"], fp, c["MUFU"], c["LDG"], c["LDGSTS"], c["LDS"], c["STS"], c["STG"],
                      c["BRA"] + c["BSSY"] + c["BSYNC"], c["WARPSYNC"] + c["BAR"]))
     rows.sort(key=lambda r: r[3])
     print("# Static resources of the fused-step kernels (`tools/sass_stats.py`, sm_100a, %s)\n" % os.path.basename(LIB))
@@ -72,7 +73,7 @@ def main():
     print("|---|---|---|---|---|---|---|---|---|---|---|---|---|")
     for r in rows:
         print("| " + " | ".join(str(x) for x in r) + " |")
-    other = [(names[k], v) for k, v in usage.items() if "mpe_kernel" not in names[k] or ", 0>" not in names[k]]
+    other = [(names[k], v) for k, v in usage.items() if "mpe_kernel" not in names[k] or ", 0, " not in names[k]]
     spills = [n for n, (r, s) in other if s]
     print("\nOther kernels with a non-zero stack frame: %s" % (", ".join("`%s`" % s for s in spills) or "none"))
 

@@ -51,7 +51,7 @@ def main():
     for sc in args.scenarios.split(","):
         spec = SCENARIOS.get(sc, dict(name=sc, kw={}))
         for n in [int(x) for x in args.sizes.split(",")]:
-            ring = bench.Ring(spec["name"], spec["kw"], n, dev, rank, world)
+            ring = bench.Ring(spec["name"], spec["kw"], n, dev, rank, world, max_ring=64)
             k = ring.R * max(1, 64 // ring.R)                 # whole ring passes, 64+ launches per graph
             plan = ring.plan(k)
             with torch.cuda.stream(ring.stream):
@@ -78,7 +78,8 @@ def main():
             total, mx, _ = aggregate_counters(n * steps, sec)
             if rank == 0:
                 per_gpu_gbs = ring.bytes_per_env * n / (mx / steps) / 1e9
-                rec = {"scenario": sc, "n_gpus": world, "n_env_per_gpu": n, "ring": ring.R, "steps": steps,
+                rec = {"scenario": sc, "n_gpus": world, "n_env_per_gpu": n, "ring": ring.R,
+                       "ring_inputs_exceed_2xL2": ring.R * ring.input_bytes_per_env * n > 2 * bench.L2_BYTES, "steps": steps,
                        "us_per_step": 1e6 * mx / steps, "env_steps_per_sec": total / mx,
                        "bytes_per_env_step": ring.bytes_per_env, "achieved_gbs_per_gpu": per_gpu_gbs, "peak_gbs": peak,
                        "frac": per_gpu_gbs / peak, "peak_source": src}
