@@ -179,6 +179,18 @@ MPE_API int mpe_step(mpe_handle h, void *agent_pv_dev, const void *lm_p_dev, flo
              const int32_t *goal_dev, const float *const *act_n_dev, float *const *obs_n_dev,
              float *rew_dev, uint8_t *done_dev, float *info_dev, uint32_t flags, void *stream);
 
+/* n_steps consecutive MultiAgentEnv.step calls (environment.py:80-104; the loop of bin/interactive.py:27-39 with the
+ * policy's outputs known in advance) on pre-generated actions, in ONE launch: act_seq_dev[i] is float
+ * [n_steps][n_env][act_dim_i].  A world's state stays in registers between the steps; per step only the actions are read.
+ * Outputs: the state after the last step, obs_n_dev / done_dev for that final state, rew_sum_dev [A][n_env] = the
+ * per-agent rewards summed over the steps in step order, and -- if rew_steps_dev is not NULL -- every step's rewards
+ * [n_steps][A][n_env].  Bit-identical to n_steps calls of mpe_step.  (CEM / MPPI style planners, evaluation of
+ * recorded action sequences.)  MPE_FLAG_DISCRETE_ACTION_INPUT is not supported here. */
+MPE_API int mpe_rollout(mpe_handle h, void *agent_pv_dev, const void *lm_p_dev, float *comm_dev,
+                        const int32_t *goal_dev, const float *const *act_seq_dev, int32_t n_steps,
+                        float *const *obs_n_dev, float *rew_sum_dev, float *rew_steps_dev, uint8_t *done_dev,
+                        uint32_t flags, void *stream);
+
 /* Same step for a caller that holds HOST buffers (what the reference's callers hold):
  * act_n_host[i] -> (async H2D into act_n_dev[i]) -> mpe_step -> (async D2H) obs_n_host[i],
  * rew_host, done_host, all ordered on `stream`.  Host buffers should be pinned for the copies

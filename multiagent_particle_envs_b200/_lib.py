@@ -83,6 +83,7 @@ _SIGNATURES = {
     "mpe_world_step": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "mpe_observe": (ctypes.c_int, [_P, _P, _P, _P, _P, _PP, _P, _P, _P, ctypes.c_uint32, _P]),
     "mpe_step": (ctypes.c_int, [_P, _P, _P, _P, _P, _PP, _PP, _P, _P, _P, ctypes.c_uint32, _P]),
+    "mpe_rollout": (ctypes.c_int, [_P, _P, _P, _P, _P, _PP, ctypes.c_int32, _PP, _P, _P, _P, ctypes.c_uint32, _P]),
     "mpe_step_host": (ctypes.c_int, [_P, _P, _P, _P, _P, _PP, _PP, _PP, _P, _P, _P, _PP, _P, _P, _P,
                                      ctypes.c_uint32, _P]),
     "mpe_strerror": (ctypes.c_char_p, [ctypes.c_int]),

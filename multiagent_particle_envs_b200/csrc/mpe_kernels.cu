@@ -62,6 +62,16 @@ struct Shape {
     }
     static constexpr int kWarpFloats = warp_floats();
     static constexpr int kWarpBytes = kWarpFloats * 4;
+    // K-step rollout: a second set of action tiles behind the regular staging (step t+1 is prefetched while step t runs)
+    static constexpr int kRolloutWarpFloats = kWarpFloats + ((obs_base() + 3) & ~3);
+    static constexpr int kRolloutWarpBytes = kRolloutWarpFloats * 4;
+    // software-pipelined persistent step (mpe_pipe_kernel): per warp [regular staging incl. obs tiles][second action
+    // region][2 x state image: pv float4 [A][32], lm float2 [L][32], goal int [G][32]]
+    static constexpr int kStateFloats = (4 * P::A + 2 * P::L + P::G) * 32;
+    static constexpr int kPipeAct1 = kWarpFloats;
+    static constexpr int kPipeState0 = kPipeAct1 + ((obs_base() + 3) & ~3);
+    static constexpr int kPipeWarpFloats = kPipeState0 + 2 * kStateFloats;
+    static constexpr int kPipeWarpBytes = kPipeWarpFloats * 4;
     static constexpr int kNC = P::NS * P::DIMC;
 };
 
@@ -111,6 +121,89 @@ __device__ __forceinline__ void physics(const DevDesc &d, typename P::W &w, cons
         const float4 r = integrate_entity<P::kSpeedLimit>(w.px[i], w.py[i], w.vx[i], w.vy[i], fx[i], fy[i], d.keep,
                                                           d.a_dt_over_mass[i], d.dt, d.a_max_speed[i]);
         w.px[i] = r.x; w.py[i] = r.y; w.vx[i] = r.z; w.vy[i] = r.w;
+    }
+}
+
+
+// MultiAgentEnv._set_action (environment.py:144-192) for this lane's world, from the warp's staged action tiles
+// (s_act = the warp's staging base; tile i starts at Shape<P>::act_off(i))
+template <class P>
+__device__ __forceinline__ void decode_rows(const float *s_act, int lane, const DevDesc &d, uint32_t flags,
+                                            float (&ux)[P::A], float (&uy)[P::A], float *cact) {
+    static_for<P::A>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        constexpr int AD = P::act_dim(i);
+        constexpr int OFF = Shape<P>::act_off(i);
+        const float *row = s_act + OFF + lane * Tile<AD>::kStride;
+        int off = 0;
+        float x = 0.0f, y = 0.0f;                                       // :145
+        if constexpr (P::movable(i)) {
+            float p0 = row[0], p1 = row[1], p2 = row[2], p3 = row[3], p4 = row[4];
+            if (flags & MPE_FLAG_FORCE_DISCRETE_ACTION) {               // :169-172 (first arg-max)
+                int best = 0;
+                float bv = p0;
+                if (p1 > bv) { bv = p1; best = 1; }
+                if (p2 > bv) { bv = p2; best = 2; }
+                if (p3 > bv) { bv = p3; best = 3; }
+                if (p4 > bv) { bv = p4; best = 4; }
+                p1 = best == 1 ? 1.0f : 0.0f; p2 = best == 2 ? 1.0f : 0.0f;
+                p3 = best == 3 ? 1.0f : 0.0f; p4 = best == 4 ? 1.0f : 0.0f;
+            }
+            x += p1 - p2;                                               // :174
+            y += p3 - p4;                                               // :175
+            // explicit multiplies: must not be contracted into the force accumulation, or the fused
+            // step would round differently from set_action -> world_step
+            x = __fmul_rn(x, d.a_sens[i]);                              // :178-181
+            y = __fmul_rn(y, d.a_sens[i]);
+            off = 5;
+        }
+        ux[i] = x;
+        uy[i] = y;
+        if constexpr (i < P::NS) {                                      // :183-190 speakers come first
+#pragma unroll
+            for (int q = 0; q < P::DIMC; ++q) cact[i * P::DIMC + q] = row[off + q];
+        }
+    });
+}
+
+// observation rows of one 32-world tile: full warps write through the warp-private tiles and stream them out as
+// coalesced 16-byte stores; the batch's last, partial warp writes its rows straight to global memory.
+// `half` < 0: every agent; 0 / 1: only the even / odd agents (warp pairs).
+template <class P>
+__device__ __forceinline__ void write_observations(const StepArgs &a, const DevDesc &d, const typename P::W &w, float *s_warp,
+                                                   int lane, int rows, bool active, int64_t w0, int64_t wi, int half) {
+    constexpr int A = P::A;
+    if (rows == 32) {
+        // Tiles are private per agent (dense ones), so no barrier is needed between agents: all rows are
+        // written, one __syncwarp, then the warp streams every tile out as 16-byte stores and retires.
+        // (A TMA bulk store was measured slower here: the warp has to stay resident until the copy
+        // engine has read its shared memory, ~1.7 us at 13 warps/SM; see profiles/.)
+        static_for<A>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            constexpr int OD = P::obs_dim(i);
+            if (half >= 0 && (i & 1) != half) return;     // warp-uniform: the partner warp writes this agent
+            TileWriter<OD> o(s_warp + Shape<P>::obs_off(i), lane);
+            P::template observe<i>(d, w, o);
+            if constexpr (!Shape<P>::obs_dense(i)) {  // padded tiles share one slot
+                __syncwarp();
+                obs_tile_store<OD>(a.obs[i] + w0 * OD, s_warp + Shape<P>::obs_off(i), lane);
+                __syncwarp();
+            }
+        });
+        __syncwarp();
+        static_for<A>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            constexpr int OD = P::obs_dim(i);
+            if (half >= 0 && (i & 1) != half) return;
+            if constexpr (Shape<P>::obs_dense(i)) obs_tile_store<OD>(a.obs[i] + w0 * OD, s_warp + Shape<P>::obs_off(i), lane);
+        });
+    } else if (active) {  // the batch's last, partial warp: rows go straight to global memory
+        static_for<A>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            if (half >= 0 && (i & 1) != half) return;
+            RowWriter o{a.obs[i] + wi * P::obs_dim(i)};
+            P::template observe<i>(d, w, o);
+        });
     }
 }
 
@@ -264,40 +357,7 @@ __global__ void __launch_bounds__(kMaxThreads, MPE_MIN_BLOCKS) mpe_kernel(const 
             });
             __syncwarp();
         }
-        static_for<A>([&](auto ic) {
-            constexpr int i = decltype(ic)::value;
-            constexpr int AD = P::act_dim(i);
-            constexpr int OFF = Shape<P>::act_off(i);
-            const float *row = s_warp + OFF + lane * Tile<AD>::kStride;
-            int off = 0;
-            float x = 0.0f, y = 0.0f;                                       // :145
-            if constexpr (P::movable(i)) {
-                float p0 = row[0], p1 = row[1], p2 = row[2], p3 = row[3], p4 = row[4];
-                if (a.flags & MPE_FLAG_FORCE_DISCRETE_ACTION) {             // :169-172 (first arg-max)
-                    int best = 0;
-                    float bv = p0;
-                    if (p1 > bv) { bv = p1; best = 1; }
-                    if (p2 > bv) { bv = p2; best = 2; }
-                    if (p3 > bv) { bv = p3; best = 3; }
-                    if (p4 > bv) { bv = p4; best = 4; }
-                    p1 = best == 1 ? 1.0f : 0.0f; p2 = best == 2 ? 1.0f : 0.0f;
-                    p3 = best == 3 ? 1.0f : 0.0f; p4 = best == 4 ? 1.0f : 0.0f;
-                }
-                x += p1 - p2;                                               // :174
-                y += p3 - p4;                                               // :175
-                // explicit multiplies: must not be contracted into the force accumulation, or the fused
-                // step would round differently from set_action -> world_step
-                x = __fmul_rn(x, d.a_sens[i]);                              // :178-181
-                y = __fmul_rn(y, d.a_sens[i]);
-                off = 5;
-            }
-            ux[i] = x;
-            uy[i] = y;
-            if constexpr (i < P::NS) {                                      // :183-190 speakers come first
-#pragma unroll
-                for (int q = 0; q < P::DIMC; ++q) cact[i * P::DIMC + q] = row[off + q];
-            }
-        });
+        decode_rows<P>(s_warp, lane, d, a.flags, ux, uy, cact);
         }   // float action vectors
         if constexpr (MODE == kSetAction) {
             if (active) {
@@ -350,38 +410,7 @@ __global__ void __launch_bounds__(kMaxThreads, MPE_MIN_BLOCKS) mpe_kernel(const 
         for (int i = 0; i < A; ++i) rew[i] = s;
     }
     if (!(a.flags & (kFlagPdlEarly | kFlagPdlAfterLoads | kFlagPdlAtExit | kFlagPdlAfterIssue))) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (rows == 32) {
-        // Tiles are private per agent (dense ones), so no barrier is needed between agents: all rows are
-        // written, one __syncwarp, then the warp streams every tile out as 16-byte stores and retires.
-        // (A TMA bulk store was measured slower here: the warp has to stay resident until the copy
-        // engine has read its shared memory, ~1.7 us at 13 warps/SM; see profiles/.)
-        static_for<A>([&](auto ic) {
-            constexpr int i = decltype(ic)::value;
-            constexpr int OD = P::obs_dim(i);
-            if (SPLIT && (i & 1) != half) return;     // warp-uniform: the partner warp writes this agent
-            TileWriter<OD> o(s_warp + Shape<P>::obs_off(i), lane);
-            P::template observe<i>(d, w, o);
-            if constexpr (!Shape<P>::obs_dense(i)) {  // padded tiles share one slot
-                __syncwarp();
-                obs_tile_store<OD>(a.obs[i] + w0 * OD, s_warp + Shape<P>::obs_off(i), lane);
-                __syncwarp();
-            }
-        });
-        __syncwarp();
-        static_for<A>([&](auto ic) {
-            constexpr int i = decltype(ic)::value;
-            constexpr int OD = P::obs_dim(i);
-            if (SPLIT && (i & 1) != half) return;
-            if constexpr (Shape<P>::obs_dense(i)) obs_tile_store<OD>(a.obs[i] + w0 * OD, s_warp + Shape<P>::obs_off(i), lane);
-        });
-    } else if (active) {  // the batch's last, partial warp: rows go straight to global memory
-        static_for<A>([&](auto ic) {
-            constexpr int i = decltype(ic)::value;
-            if (SPLIT && (i & 1) != half) return;
-            RowWriter o{a.obs[i] + wi * P::obs_dim(i)};
-            P::template observe<i>(d, w, o);
-        });
-    }
+    write_observations<P>(a, d, w, s_warp, lane, rows, active, w0, wi, SPLIT ? half : -1);
     if (active && (!SPLIT || half == 1)) {
 #pragma unroll
         for (int i = 0; i < A; ++i) {
@@ -391,6 +420,246 @@ __global__ void __launch_bounds__(kMaxThreads, MPE_MIN_BLOCKS) mpe_kernel(const 
         if (P::INFO > 0 && a.info != nullptr) {
 #pragma unroll
             for (int q = 0; q < P::INFO * A; ++q) a.info[q * n + wi] = info[q];
+        }
+    }
+}
+
+
+
+// ---- software-pipelined persistent fused step (MPE_B200_PIPE=1) -------------------------
+// A grid of (tiles / tiles-per-warp) warps; every warp walks its 32-world tiles with a two-deep pipeline: ALL inputs
+// of tile k+1 (action tiles, agent state, landmarks, goal indices) are fetched with cp.async into the second half of
+// the warp's staging while tile k is decoded, integrated, observed and streamed out.  Load, compute and store phases
+// of different tiles overlap inside one strictly ordered launch.  Same arithmetic functions as mpe_kernel: results
+// are bit-identical (tests/test_gpu_parity.py).  Full tiles only; the launcher sends a ragged tail to mpe_kernel.
+template <class P>
+__global__ void __launch_bounds__(kMaxThreads, MPE_MIN_BLOCKS) mpe_pipe_kernel(const __grid_constant__ StepArgs a) {
+    constexpr int A = P::A, L = P::L, NC = Shape<P>::kNC;
+    using S = Shape<P>;
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t n = a.n;
+    const int64_t n_tiles = a.count >> 5;
+    const int64_t nwarps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+    int64_t t = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + warp;
+    float *s_warp = smem + warp * S::kPipeWarpFloats;
+    const DevDesc &d = a.d;
+    {
+        uintptr_t touch = reinterpret_cast<uintptr_t>(a.pv) ^ reinterpret_cast<uintptr_t>(a.lm) ^
+                          reinterpret_cast<uintptr_t>(a.obs[0]) ^ reinterpret_cast<uintptr_t>(a.rew) ^ a.flags ^
+                          __float_as_uint(d.dt) ^ __float_as_uint(d.a_size[0]);
+        asm volatile("" ::"l"(touch));
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (t >= n_tiles) return;
+
+    auto act_base = [&](int b) { return s_warp + b * S::kPipeAct1; };
+    auto state_base = [&](int b) { return s_warp + S::kPipeState0 + b * S::kStateFloats; };
+    auto prefetch = [&](int64_t tile, int b) {
+        const int64_t w0 = a.begin + tile * 32;
+        float *ab = act_base(b);
+        static_for<A>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            constexpr int AD = P::act_dim(i), kVec = 32 * AD / 4;
+            const float *g = a.act[i] + w0 * AD;
+            float *sdst = ab + S::act_off(i);
+#pragma unroll
+            for (int q0 = 0; q0 < kVec; q0 += 32)
+                if (q0 + 32 <= kVec || q0 + lane < kVec) cp_async16(sdst + 4 * (q0 + lane), g + 4 * (q0 + lane));
+        });
+        float *sb = state_base(b);
+#pragma unroll
+        for (int i = 0; i < A; ++i) cp_async16(sb + (i * 32 + lane) * 4, a.pv + i * n + w0 + lane);
+#pragma unroll
+        for (int l = 0; l < L; ++l) cp_async8(sb + A * 128 + (l * 32 + lane) * 2, a.lm + l * n + w0 + lane);
+#pragma unroll
+        for (int q = 0; q < P::G; ++q) cp_async4(sb + A * 128 + L * 64 + q * 32 + lane, a.goal + q * n + w0 + lane);
+    };
+
+    prefetch(t, 0);
+    cp_async_commit();
+    bool first = true;
+#pragma unroll 1
+    for (int b = 0; t < n_tiles; t += nwarps, b ^= 1) {
+        const int64_t w0 = a.begin + t * 32, wi = w0 + lane;
+        if (t + nwarps < n_tiles) prefetch(t + nwarps, b ^ 1);
+        cp_async_commit();
+        cp_async_wait_group<1>();
+        __syncwarp();
+        if (first && (a.flags & kFlagPdlAfterLoads)) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        first = false;
+        typename P::W w;
+        const float *sb = state_base(b);
+#pragma unroll
+        for (int i = 0; i < A; ++i) {
+            const float4 v = *reinterpret_cast<const float4 *>(sb + (i * 32 + lane) * 4);
+            w.px[i] = v.x; w.py[i] = v.y; w.vx[i] = v.z; w.vy[i] = v.w;
+        }
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+            const float2 v = *reinterpret_cast<const float2 *>(sb + A * 128 + (l * 32 + lane) * 2);
+            w.lx[l] = v.x; w.ly[l] = v.y;
+        }
+        if constexpr (P::G > 0) {
+#pragma unroll
+            for (int q = 0; q < P::G; ++q) w.g[q] = reinterpret_cast<const int *>(sb + A * 128 + L * 64)[q * 32 + lane];
+        }
+        float ux[A], uy[A];
+        float cact[NC > 0 ? NC : 1];
+        decode_rows<P>(act_base(b), lane, d, a.flags, ux, uy, cact);
+        physics<P>(d, w, ux, uy);
+#pragma unroll
+        for (int q = 0; q < NC; ++q) w.c[q] = cact[q];
+#pragma unroll
+        for (int i = 0; i < A; ++i)
+            if (P::movable(i)) a.pv[i * n + wi] = make_float4(w.px[i], w.py[i], w.vx[i], w.vy[i]);
+#pragma unroll
+        for (int q = 0; q < NC; ++q) a.comm[q * n + wi] = w.c[q];
+        float rew[A];
+        float info[(P::INFO > 0 ? P::INFO : 1) * A];
+        P::prepare(d, w);
+        P::reward(d, w, rew, (P::INFO > 0 && a.info != nullptr) ? info : nullptr);
+        if (a.flags & MPE_FLAG_SHARED_REWARD) {
+            float sum = 0.0f;
+#pragma unroll
+            for (int i = 0; i < A; ++i) sum += rew[i];
+#pragma unroll
+            for (int i = 0; i < A; ++i) rew[i] = sum;
+        }
+        write_observations<P>(a, d, w, s_warp, lane, 32, true, w0, wi, -1);
+#pragma unroll
+        for (int i = 0; i < A; ++i) {
+            a.rew[i * n + wi] = rew[i];
+            a.done[i * n + wi] = 0;
+        }
+        if (P::INFO > 0 && a.info != nullptr) {
+#pragma unroll
+            for (int q = 0; q < P::INFO * A; ++q) a.info[q * n + wi] = info[q];
+        }
+        __syncwarp();   // every lane is done with buffer b (inputs) and the obs tiles before they are reused
+    }
+}
+
+// ---- K-step open-loop rollout (the persistent multi-step form) --------------------------
+// T consecutive MultiAgentEnv.step calls on pre-generated actions act[i] : [T][n_env][act_dim_i] in ONE launch: a
+// world's state is loaded once, lives in registers for all T steps and is written once; per step only the actions are
+// read (the next step's tiles are prefetched with cp.async while this step computes) and, optionally, the per-step
+// rewards written.  Observations are produced for the final state only.  This is what sampling-based planners (CEM /
+// MPPI: score many candidate action sequences by their return) and policy evaluation on recorded actions need; HBM
+// traffic per env-step drops from 411 B to 60 (+12) B for simple_spread N=3.  Bit-identical to T launches of the
+// fused step with rewards summed in step order (tests/test_gpu_api.py).
+struct RolloutArgs {
+    StepArgs s;
+    int32_t T;
+    float *rew_steps;   // [T][A][n] per-step rewards (after the shared-reward sum), or null
+};
+
+template <class P>
+__global__ void __launch_bounds__(kMaxThreads, MPE_MIN_BLOCKS) mpe_rollout_kernel(const __grid_constant__ RolloutArgs ra) {
+    constexpr int A = P::A, L = P::L, NC = Shape<P>::kNC;
+    const StepArgs &a = ra.s;
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t n = a.n;
+    const int64_t end = a.begin + a.count;
+    const int64_t w0 = a.begin + (static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + warp) * 32;
+    if (w0 >= end) return;
+    const int rows = (end - w0) < 32 ? static_cast<int>(end - w0) : 32;
+    const bool active = lane < rows;
+    const int64_t wi = w0 + (active ? lane : 0);
+    float *s_warp = smem + warp * Shape<P>::kRolloutWarpFloats;
+    const DevDesc &d = a.d;
+    uintptr_t bits = 0;
+#pragma unroll
+    for (int i = 0; i < A; ++i) bits |= reinterpret_cast<uintptr_t>(a.act[i]) | static_cast<uintptr_t>((n * P::act_dim(i) * 4) & 15);
+    const bool fast = Shape<P>::all_act_dense() && rows == 32 && (bits & 15u) == 0;   // warp-uniform
+
+    auto stage = [&](int t, float *base) {   // action tiles of step t -> base (asynchronously on the fast path)
+        static_for<A>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            constexpr int AD = P::act_dim(i), kVec = 32 * AD / 4;
+            const float *g = a.act[i] + (static_cast<int64_t>(t) * n + w0) * AD;
+            float *sdst = base + Shape<P>::act_off(i);
+            if (fast) {
+#pragma unroll
+                for (int q0 = 0; q0 < kVec; q0 += 32)
+                    if (q0 + 32 <= kVec || q0 + lane < kVec) cp_async16(sdst + 4 * (q0 + lane), g + 4 * (q0 + lane));
+            } else {
+                tile_load<AD>(sdst, g, rows, lane);
+            }
+        });
+    };
+    stage(0, s_warp);
+    cp_async_commit();
+
+    typename P::W w;
+#pragma unroll
+    for (int i = 0; i < A; ++i) {
+        const float4 v = state_load(a.pv + i * n + wi);
+        w.px[i] = v.x; w.py[i] = v.y; w.vx[i] = v.z; w.vy[i] = v.w;
+    }
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+        const float2 v = state_load(a.lm + l * n + wi);
+        w.lx[l] = v.x; w.ly[l] = v.y;
+    }
+    if constexpr (NC > 0) {   // only matters for T == 0; every step overwrites it (update_agent_state)
+#pragma unroll
+        for (int q = 0; q < NC; ++q) w.c[q] = a.comm[q * n + wi];
+    }
+    if constexpr (P::G > 0) {
+#pragma unroll
+        for (int q = 0; q < P::G; ++q) w.g[q] = a.goal[q * n + wi];
+    }
+
+    float rsum[A];
+#pragma unroll
+    for (int i = 0; i < A; ++i) rsum[i] = 0.0f;
+#pragma unroll 1
+    for (int t = 0; t < ra.T; ++t) {
+        float *cur = s_warp + (t & 1) * Shape<P>::kWarpFloats;           // tiles of step t; step t+1 goes to the other half
+        if (t + 1 < ra.T) stage(t + 1, s_warp + ((t + 1) & 1) * Shape<P>::kWarpFloats);
+        cp_async_commit();                 // possibly empty: keeps "all but the newest group" == "step t has landed"
+        cp_async_wait_group<1>();
+        __syncwarp();
+        float ux[A], uy[A];
+        float cact[NC > 0 ? NC : 1];
+        decode_rows<P>(cur, lane, d, a.flags, ux, uy, cact);
+        __syncwarp();                      // every lane has read `cur` before step t+2 is staged into it
+        physics<P>(d, w, ux, uy);
+#pragma unroll
+        for (int q = 0; q < NC; ++q) w.c[q] = cact[q];
+        float rew[A];
+        P::reward(d, w, rew, nullptr);
+        if (a.flags & MPE_FLAG_SHARED_REWARD) {
+            float sum = 0.0f;
+#pragma unroll
+            for (int i = 0; i < A; ++i) sum += rew[i];
+#pragma unroll
+            for (int i = 0; i < A; ++i) rew[i] = sum;
+        }
+#pragma unroll
+        for (int i = 0; i < A; ++i) rsum[i] = __fadd_rn(rsum[i], rew[i]);
+        if (ra.rew_steps != nullptr && active) {
+#pragma unroll
+            for (int i = 0; i < A; ++i) ra.rew_steps[(static_cast<int64_t>(t) * A + i) * n + wi] = rew[i];
+        }
+    }
+    cp_async_wait_all();
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < A; ++i)
+            if (P::movable(i)) a.pv[i * n + wi] = make_float4(w.px[i], w.py[i], w.vx[i], w.vy[i]);
+#pragma unroll
+        for (int q = 0; q < NC; ++q) a.comm[q * n + wi] = w.c[q];
+    }
+    P::prepare(d, w);
+    write_observations<P>(a, d, w, s_warp, lane, rows, active, w0, wi, -1);
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < A; ++i) {
+            a.rew[i * n + wi] = rsum[i];
+            a.done[i * n + wi] = 0;
         }
     }
 }
@@ -593,6 +862,10 @@ struct Program {
     KernelFn fn[4];
     int smem_bytes;  // dynamic shared memory per WARP
     KernelFn split_fn;  // fused step with a warp PAIR per 32-world tile (small batches of heavy scenarios)
+    KernelFn pipe_fn;   // software-pipelined persistent fused step (null unless every action tile is dense)
+    int pipe_smem;      // dynamic shared memory per WARP of the pipelined kernel
+    void (*rollout_fn)(RolloutArgs);   // K-step open-loop rollout
+    int rollout_smem;   // dynamic shared memory per WARP of the rollout kernel
     KernelFn lanes_fn;  // lane-per-agent fused step (simple_spread only), else null
     int lanes_smem, lanes_wpw;
     int A, L, NS, DIMC, INFO, G;
@@ -610,6 +883,10 @@ static Program make_program() {
     p.fn[kWorldStep] = mpe_kernel<P, kWorldStep>;
     p.fn[kObserve] = mpe_kernel<P, kObserve>;
     p.split_fn = P::A >= 2 ? mpe_kernel<P, kFusedStep, true> : nullptr;
+    p.pipe_fn = Shape<P>::all_act_dense() ? mpe_pipe_kernel<P> : nullptr;
+    p.pipe_smem = Shape<P>::kPipeWarpBytes;
+    p.rollout_fn = mpe_rollout_kernel<P>;
+    p.rollout_smem = Shape<P>::kRolloutWarpBytes;
     p.smem_bytes = Shape<P>::kWarpBytes;  // per warp
     p.A = P::A; p.L = P::L; p.NS = P::NS; p.DIMC = P::DIMC; p.INFO = P::INFO; p.G = P::G;
     for (int i = 0; i < P::A; ++i) { p.obs_dim[i] = P::obs_dim(i); p.act_dim[i] = P::act_dim(i); }
@@ -738,6 +1015,12 @@ extern "C" int mpe_create(const mpe_desc *desc, int64_t n_env, int device, mpe_h
                                               prog->smem_bytes * max_warps_per_block(prog->smem_bytes)));
         if (prog->lanes_fn)
             CUDA_TRY(cudaFuncSetAttribute(prog->lanes_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, prog->lanes_smem * 4));
+        if (prog->pipe_fn)
+            CUDA_TRY(cudaFuncSetAttribute(prog->pipe_fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          prog->pipe_smem * max_warps_per_block(prog->pipe_smem)));
+        if (prog->rollout_fn)
+            CUDA_TRY(cudaFuncSetAttribute(prog->rollout_fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          prog->rollout_smem * max_warps_per_block(prog->rollout_smem)));
         if (prog->split_fn && prog->smem_bytes > 0)
             CUDA_TRY(cudaFuncSetAttribute(prog->split_fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           prog->smem_bytes * max_warps_per_block(prog->smem_bytes)));
@@ -886,6 +1169,47 @@ static int launch(mpe_handle h, int mode, StepArgs &args, void *stream, int64_t 
         __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED);
         return MPE_OK;
     }
+    // Software-pipelined persistent kernel (mpe_pipe_kernel): MPE_B200_PIPE=1, MPE_B200_PIPE_TPW tiles per warp (default 2)
+    static const int pipe_env = [] { const char *e = getenv("MPE_B200_PIPE"); return e ? atoi(e) : 0; }();
+    static const int pipe_tpw = [] { const char *e = getenv("MPE_B200_PIPE_TPW"); int v = e ? atoi(e) : 2; return v < 1 ? 1 : v; }();
+    if (pipe_env == 1 && mode == kFusedStep && h->prog->pipe_fn != nullptr && args.count >= 32 &&
+        !(args.flags & MPE_FLAG_DISCRETE_ACTION_INPUT)) {
+        bool aligned = true;
+        for (int i = 0; i < h->prog->A; ++i)
+            aligned = aligned && ((reinterpret_cast<uintptr_t>(args.act[i]) + static_cast<uintptr_t>(begin) * h->prog->act_dim[i] * 4) & 15u) == 0;
+        if (aligned && (begin % 32) == 0 && (h->n % 4) == 0) {
+            const int64_t tiles = args.count / 32, tail = args.count - tiles * 32;
+            static const int pwpb_env = [] { const char *e = getenv("MPE_B200_WPB"); int v = e ? atoi(e) : 0; return (v >= 1 && v <= kMaxWarpsPerBlock) ? v : 0; }();
+            int pwpb = pwpb_env ? pwpb_env : 2;
+            if (pwpb > max_warps_per_block(h->prog->pipe_smem)) pwpb = max_warps_per_block(h->prog->pipe_smem);
+            const int64_t pwarps = (tiles + pipe_tpw - 1) / pipe_tpw;
+            const int64_t pblocks = (pwarps + pwpb - 1) / pwpb;
+            int prev = 0;
+            CUDA_TRY(cudaGetDevice(&prev));
+            if (prev != h->device) CUDA_TRY(cudaSetDevice(h->device));
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(static_cast<unsigned>(pblocks));
+            cfg.blockDim = dim3(32 * pwpb);
+            cfg.dynamicSmemBytes = static_cast<size_t>(h->prog->pipe_smem) * pwpb;
+            cfg.stream = static_cast<cudaStream_t>(stream);
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = pdl_mode() ? 1 : 0;
+            StepArgs pa = args;
+            pa.count = tiles * 32;
+            if (pdl_mode() == 3) pa.flags |= kFlagPdlAfterLoads;
+            void *params[] = {&pa};
+            cudaError_t e = cudaLaunchKernelExC(&cfg, reinterpret_cast<const void *>(h->prog->pipe_fn), params);
+            if (prev != h->device) cudaSetDevice(prev);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelExC(pipe)");
+            __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED);
+            if (tail == 0) return MPE_OK;
+            args.begin = begin + tiles * 32;      // the ragged tail goes through the regular kernel below
+            args.count = tail;
+        }
+    }
     int64_t warps = (args.count + 31) / 32;
     // Warp pairs (see mpe_kernel<..., SPLIT>): MPE_B200_SPLIT = 0 never, 1 always, unset: when one warp per tile leaves
     // the machine under ~2.5 warps per scheduler AND the scenario is heavy enough (>= 4 agents) for instruction
@@ -1023,6 +1347,49 @@ extern "C" int mpe_step(mpe_handle h, void *pv, const void *lm, float *comm, con
     if (r) return r;
     a.flags = flags;
     return launch(h, kFusedStep, a, stream);
+}
+
+extern "C" int mpe_rollout(mpe_handle h, void *pv, const void *lm, float *comm, const int32_t *goal,
+                           const float *const *act_seq, int32_t n_steps, float *const *obs_n, float *rew_sum,
+                           float *rew_steps, uint8_t *done, uint32_t flags, void *stream) {
+    if (!h || n_steps < 0) return MPE_ERR_BAD_ARG;
+    if (h->device < 0) return MPE_ERR_NO_DEVICE;
+    if (h->prog->scenario == MPE_SCN_CUSTOM || h->prog->rollout_fn == nullptr) return MPE_ERR_UNSUPPORTED;
+    if (flags & MPE_FLAG_DISCRETE_ACTION_INPUT) return MPE_ERR_UNSUPPORTED;
+    if (rew_steps != nullptr && !ok4(rew_steps)) return MPE_ERR_BAD_ARG;
+    NvtxRange range("mpe_rollout");
+    RolloutArgs ra{};
+    StepArgs &a = ra.s;
+    int r = fill_state(h, a, pv, lm, comm, goal);
+    if (r) return r;
+    r = fill_actions(h, a, act_seq);
+    if (r) return r;
+    r = fill_outputs(h, a, obs_n, rew_sum, done, nullptr);
+    if (r) return r;
+    a.info = nullptr;
+    a.flags = flags;
+    a.d = h->dev;
+    a.n = h->n;
+    a.begin = 0;
+    a.count = h->n;
+    ra.T = n_steps;
+    ra.rew_steps = rew_steps;
+    const int64_t warps = (h->n + 31) / 32;
+    int wpb = warps <= 148 * 4 ? 1 : (warps <= 148 * 64 ? 2 : 4);
+    if (wpb > max_warps_per_block(h->prog->rollout_smem)) wpb = max_warps_per_block(h->prog->rollout_smem);
+    const int64_t blocks = (warps + wpb - 1) / wpb;
+    if (blocks > 0x7fffffffLL) return MPE_ERR_BAD_ARG;
+    int prev = 0;
+    CUDA_TRY(cudaGetDevice(&prev));
+    if (prev != h->device) CUDA_TRY(cudaSetDevice(h->device));
+    void *params[] = {&ra};
+    cudaError_t e = cudaLaunchKernel(reinterpret_cast<const void *>(h->prog->rollout_fn), dim3(static_cast<unsigned>(blocks)),
+                                     dim3(32 * wpb), params, static_cast<size_t>(h->prog->rollout_smem) * wpb,
+                                     static_cast<cudaStream_t>(stream));
+    if (prev != h->device) cudaSetDevice(prev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernel(rollout)");
+    __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED);
+    return MPE_OK;
 }
 
 // adjacent (dst, src, bytes) copies with equal small gaps on both sides are issued as one DMA

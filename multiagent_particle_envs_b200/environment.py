@@ -198,6 +198,48 @@ class MultiAgentEnv(_Env):
         as_numpy = not hasattr(action_n[0], "dim")
         return self._pack_batched(nw, hout, as_numpy=as_numpy)
 
+    # ---- K-step open-loop rollout (batch extension) -------------------------
+    def rollout(self, action_seq_n, per_step_rewards=False):
+        """T consecutive `step` calls on pre-generated actions in ONE kernel launch (mpe_rollout): the loop of
+        bin/interactive.py:27-39 when the actions are known in advance (recorded trajectories, CEM / MPPI candidate
+        sequences).  action_seq_n[i]: float32 CUDA tensor [T, N, act_dim_i].  Returns (obs_n, reward_sum_n, done_n,
+        info_n) for the state after the last step -- reward_sum_n[i] is the sum over the T steps, bit-equal to calling
+        `step` T times and adding the rewards in order -- plus, with per_step_rewards=True, a fifth item: the [T, n, N]
+        tensor of every step's rewards.  Batched CUDA mode only."""
+        import torch
+        world = self.world
+        if not world.batched:
+            raise ValueError("rollout needs a batched env (make_env(..., num_envs=N))")
+        if self._custom:
+            raise NotImplementedError("rollout is not available for user scenarios (TorchScenario)")
+        if self.discrete_action_input:
+            raise NotImplementedError("rollout takes action vectors, not integer actions")
+        if len(action_seq_n) != self.n:
+            raise ValueError("expected %d action sequences, got %d" % (self.n, len(action_seq_n)))
+        nw = world.bind()
+        N = nw.n_env
+        T = int(action_seq_n[0].shape[0])
+        seqs = []
+        for i, a in enumerate(action_seq_n):
+            if not (torch.is_tensor(a) and a.is_cuda and a.device == nw.device):
+                raise ValueError("action_seq_n[%d] must be a CUDA tensor on %s" % (i, nw.device))
+            if tuple(a.shape) != (T, N, self._act_dims[i]):
+                raise ValueError("action_seq_n[%d] must have shape (%d, %d, %d), got %s"
+                                 % (i, T, N, self._act_dims[i], tuple(a.shape)))
+            if a.dtype != torch.float32 or not a.is_contiguous():
+                a = a.to(torch.float32).contiguous()
+            seqs.append(a)
+        out = nw.out if self.reuse_buffers else nw.new_outputs()
+        rew_steps = torch.empty((T, self.n, N), dtype=torch.float32, device=nw.device) if per_step_rewards else None
+        nw.rollout(_lib.ptr_array([t.data_ptr() for t in seqs]), T, out, self._flags(), rew_steps)
+        self._last_out = out
+        world._obs_valid = False
+        obs_n, reward_n, done_n = list(out.obs), list(out.rew_list), list(out.done_list)
+        info_n = {'n': [{} for _ in range(self.n)]}
+        if per_step_rewards:
+            return obs_n, reward_n, done_n, info_n, rew_steps
+        return obs_n, reward_n, done_n, info_n
+
     # ---- user scenarios: native _set_action + World.step, callbacks in the user's torch code -------
     def _step_custom(self, action_n, nw, flags):
         import torch

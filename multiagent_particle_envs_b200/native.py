@@ -250,6 +250,17 @@ class NativeWorld(ShapeHandle):
               "mpe_step")
         return out
 
+    def rollout(self, act_seq_ptrs, n_steps, out=None, flags=0, rew_steps=None):
+        """n_steps fused steps on pre-generated actions in ONE launch (mpe_rollout): the state stays in registers
+        between the steps.  out.obs / out.done describe the final state, out.rew holds the summed rewards;
+        rew_steps: optional float32 [n_steps, A, N] CUDA tensor receiving every step's rewards."""
+        out = out or self.out
+        pv, lm, comm, goal = self._state_ptrs()
+        check(self.lib.mpe_rollout(self.handle, pv, lm, comm, goal, act_seq_ptrs, int(n_steps), out.obs_ptrs, out.rew_ptr,
+                                   rew_steps.data_ptr() if rew_steps is not None else None, out.done_ptr, flags,
+                                   self._stream()), "mpe_rollout")
+        return out
+
     # ---- host callers (what the reference's callers hold: NumPy arrays) -----------------------
     def host_staging(self):
         if self._host is None:

@@ -207,3 +207,42 @@ def test_graphed_rollout_with_resets_draws_fresh_episodes_on_replay():
     assert float(nw.agent_pv[:, :, 2:4].abs().max()) == 0.0      # ... and the episode really was reset
     env.reset()                                                  # eager resets keep advancing the same counter
     assert int(nw._epoch_dev.item()) == e1 + 2
+
+
+@pytest.mark.parametrize("tag,n,T", [("simple_spread_n3", 2049, 25), ("simple_tag", 4096, 10), ("simple_world_comm", 1031, 7),
+                                     ("simple_reference", 512, 6), ("simple_speaker_listener", 100, 5),
+                                     ("simple_crypto", 333, 4), ("simple_adversary", 64, 9), ("simple", 33, 3)])
+def test_open_loop_rollout_equals_repeated_steps(tag, n, T):
+    """env.rollout (mpe_rollout: T steps in one launch, state in registers, next step's actions prefetched) is
+    bit-identical to T calls of env.step on the same actions with the rewards summed in step order -- full tiles take
+    the cp.async path, the ragged last tile the scalar one"""
+    env_a = make_product_env(tag, num_envs=n, seed=5)
+    env_b = make_product_env(tag, num_envs=n, seed=5)
+    env_a.reset()
+    env_b.reset()
+    na, nb = env_a.world.native, env_b.world.native
+    assert torch.equal(na.agent_pv, nb.agent_pv) and torch.equal(na.goal, nb.goal)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    seqs = []
+    for d, ag in zip(na.act_dims, env_a.agents):
+        parts = [torch.softmax(2 * torch.randn(T, n, 5, device="cuda", generator=g), -1)] if ag.movable else []
+        if d - (5 if ag.movable else 0) > 0:
+            parts.append(torch.rand(T, n, d - (5 if ag.movable else 0), device="cuda", generator=g))
+        seqs.append(torch.cat(parts, -1).contiguous())
+    obs_r, rew_r, done_r, info_r, steps_r = env_a.rollout(seqs, per_step_rewards=True)
+    rew_sum = torch.zeros(env_b.n, n, device="cuda")
+    for t in range(T):
+        obs_s, rew_s, done_s, _ = env_b.step([s[t] for s in seqs])
+        rew_sum += torch.stack(list(rew_s))
+        assert torch.equal(steps_r[t], torch.stack(list(rew_s))), t
+    torch.cuda.synchronize()
+    assert torch.equal(na.agent_pv, nb.agent_pv) and torch.equal(na.comm, nb.comm)
+    for x, y in zip(obs_r, obs_s):
+        assert torch.equal(x, y)
+    assert torch.equal(torch.stack(list(rew_r)), rew_sum)
+    assert not any(bool(d.any()) for d in done_r)
+    # without the per-step record the result is the same
+    env_c = make_product_env(tag, num_envs=n, seed=5)
+    env_c.reset()
+    obs_c, rew_c, _, _ = env_c.rollout(seqs)
+    assert all(torch.equal(x, y) for x, y in zip(obs_c, obs_r)) and torch.equal(torch.stack(list(rew_c)), rew_sum)

@@ -375,18 +375,27 @@ np.savez(sys.argv[1], **out)
 """
 
 
-def test_warp_pair_split_kernel_is_bit_identical(tmp_path):
+@pytest.mark.parametrize("variant", ["MPE_B200_SPLIT", "MPE_B200_PIPE"])
+def test_alternative_step_kernels_are_bit_identical(tmp_path, variant):
     """MPE_B200_SPLIT=1 runs every fused step with a warp PAIR per 32-world tile (both warps do the physics, each
-    writes half of the outputs; the in-place state update is ordered by a pair barrier).  Three consecutive steps
-    of eight scenarios with ragged batch sizes must equal the one-warp-per-tile kernel bit for bit."""
+    writes half of the outputs; the in-place state update is ordered by a pair barrier).  MPE_B200_PIPE=1 runs the
+    software-pipelined persistent kernel (all inputs of the next tile prefetched with cp.async; ragged tails go to the
+    regular kernel).  Three consecutive steps of eight scenarios with ragged batch sizes must equal the default
+    one-warp-per-tile kernel bit for bit."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = {}
     for mode in ("0", "1"):
-        path = str(tmp_path / ("split%s.npz" % mode))
-        env = dict(os.environ, MPE_B200_SPLIT=mode)
+        path = str(tmp_path / ("alt%s.npz" % mode))
+        env = dict(os.environ)
+        env.pop("MPE_B200_SPLIT", None)
+        env.pop("MPE_B200_PIPE", None)
+        if mode == "1":
+            env[variant] = "1"
+        else:
+            env["MPE_B200_SPLIT"] = "0"      # the reference run: plain one-warp-per-tile kernel at every size
         subprocess.run([sys.executable, "-c", _SPLIT_SCRIPT % {"root": root}, path], check=True, env=env, timeout=900)
         res[mode] = dict(np.load(path))
     assert set(res["0"]) == set(res["1"]) and len(res["0"]) >= 40
