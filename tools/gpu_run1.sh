@@ -21,6 +21,16 @@ ncu -i $O/r2a_spread3_65536_full.ncu-rep --page details > $O/r2a_ncu_details_spr
 for sp in 0 1; do
   MPE_B200_SPLIT=$sp timeout 900 python tools/sweep.py --scenarios simple_world_comm,simple_spread_n6,simple_tag,simple_spread --sizes 8192,32768,65536,131072,262144 --out $O/r2a_sweep_split$sp.jsonl > $O/r2a_sweep_split$sp.log 2>&1
 done
+# software-pipelined persistent kernel A/B
+for tpw in 2 3 4; do
+  MPE_B200_SPLIT=0 MPE_B200_PIPE=1 MPE_B200_PIPE_TPW=$tpw timeout 600 python tools/sweep.py --scenarios simple_spread,simple_tag --sizes 65536,262144 --out $O/r2a_sweep_pipe_tpw$tpw.jsonl > $O/r2a_sweep_pipe_tpw$tpw.log 2>&1
+done
+MPE_B200_SPLIT=0 MPE_B200_PIPE=1 MPE_B200_WPB=1 timeout 600 python tools/sweep.py --scenarios simple_spread --sizes 65536 --out $O/r2a_sweep_pipe_wpb1.jsonl > $O/r2a_sweep_pipe_wpb1.log 2>&1
+MPE_B200_SPLIT=0 MPE_B200_PIPE=1 MPE_B200_WPB=4 timeout 600 python tools/sweep.py --scenarios simple_spread --sizes 65536 --out $O/r2a_sweep_pipe_wpb4.jsonl > $O/r2a_sweep_pipe_wpb4.log 2>&1
+# K-step rollout kernel vs K fused steps
+for sc in simple_spread simple_tag simple_world_comm; do
+  timeout 600 python tools/rollout_bench.py --scenario $sc --num-envs 65536 >> $O/r2a_rollout_bench.jsonl 2>> $O/r2a_rollout_bench.err
+done
 # racecheck / memcheck of the warp-pair kernel
 cat > /tmp/split_small.py <<'PY'
 import sys, torch
