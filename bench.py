@@ -82,10 +82,13 @@ def shapes_from_oracle(desc):
 
 
 MAX_RING = 256      # tiny batches (< ~8k worlds) would need thousands of ring slots; they are launch-bound anyway
+L2_MULTIPLE = 8     # ring inputs >= 8 x L2.  Measured (profiles/traffic.json): with the contract's minimum of 2 x L2 the
+#                     126 MB L2 still served ~60 % of the input reads, because the evict-first observation stores leave
+#                     the input lines resident and the replacement is not LRU; 8 x L2 + a read-flush before the region
 
 
-def ring_size(input_bytes_per_env, n_env, requested=0, cap=MAX_RING):
-    need = int(2 * L2_BYTES / (input_bytes_per_env * n_env)) + 1
+def ring_size(input_bytes_per_env, n_env, requested=0, cap=MAX_RING, l2_multiple=L2_MULTIPLE):
+    need = int(l2_multiple * L2_BYTES / (input_bytes_per_env * n_env)) + 1
     return max(3, min(need, cap), requested or 0)
 
 
@@ -96,11 +99,12 @@ def workload_config(scenario, kw, n_env, n_agents, bytes_per_env, input_bytes_pe
             "scenario": scenario, "scenario_kwargs": kw, "n_env_per_gpu": n_env, "global_n_env": n_env * n_gpus,
             "agents": n_agents, "episode_length": EPISODE, "ring_batches": ring,
             "bytes_per_env_step": bytes_per_env, "input_bytes_per_env_step": input_bytes_per_env,
-            "l2_policy": "inputs larger than L2: steps rotate over %d independent batches; their INPUTS alone (state + "
-                         "actions, %.1f MB per batch) total %.0f MB %s 2 x 126 MB L2, all bytes %.0f MB"
+            "l2_policy": "inputs larger than L2 AND L2 flushed: steps rotate over %d independent batches; their INPUTS alone "
+                         "(state + actions, %.1f MB per batch) total %.0f MB %s %d x 126 MB L2 (all bytes %.0f MB), and a "
+                         "512 MB read-only sweep evicts the L2 right before every timed region"
                          % (ring, input_bytes_per_env * n_env / 1e6, ring * input_bytes_per_env * n_env / 1e6,
-                            ">" if ring * input_bytes_per_env * n_env > 2 * L2_BYTES else "(ring capped) <",
-                            ring * bytes_per_env * n_env / 1e6),
+                            ">=" if ring * input_bytes_per_env * n_env >= L2_MULTIPLE * L2_BYTES else "(ring capped) <",
+                            L2_MULTIPLE, ring * bytes_per_env * n_env / 1e6),
             "actions": "softmax of N(0,1) logits (+ uniform utterances), pre-generated per batch, resident in HBM",
             "parallelism": "dp%d (independent shards, no data-path collective)" % n_gpus}
 
@@ -439,6 +443,7 @@ class Ring(object):
         self.side = torch.cuda.Stream(dev)
         self.launches = 0
         self._graphs = {}
+        self._flush = torch.zeros(512 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
         with torch.cuda.stream(self.stream):
             for i in range(self.R):      # first launches outside capture (module load, lazy init)
                 self.step_slot(i)
@@ -455,16 +460,30 @@ class Ring(object):
             nw.reset()
             self.launches += 1
 
+    def flush_l2(self):
+        """read-only sweep over 512 MB: the L2 ends up full of CLEAN lines of a buffer nobody touches again (a write
+        sweep would leave 126 MB of dirty lines whose write-back competes with the timed steps)"""
+        self._flush.sum()
+
     def _capture(self, first, count, two_streams):
         """one CUDA graph stepping slots first .. first+count-1 (mod R), strictly in order on one stream, or with
-        even / odd positions on two streams (fork / join) for the two-batches-in-flight extra"""
+        even / odd positions on two streams (fork / join) for the two-batches-in-flight extra.  The graph records an
+        external timing event before its first and after its last kernel, so a region that consists of ONE graph
+        launch is timed inside the graph: the device-side cost of the graph launch itself (tens of microseconds,
+        dominant when K = 20) is not part of the K steps."""
         key = (first % self.R, count, two_streams)
         if key in self._graphs:
             return self._graphs[key]
         torch = self.torch
         before = self.launches
         graph = torch.cuda.CUDAGraph()
+        try:
+            graph.ev = (torch.cuda.Event(enable_timing=True, external=True), torch.cuda.Event(enable_timing=True, external=True))
+        except TypeError:       # older torch: no external events, fall back to events around the launch
+            graph.ev = None
         with torch.cuda.graph(graph, stream=self.stream):
+            if graph.ev:
+                graph.ev[0].record(self.stream)
             if two_streams:
                 self.side.wait_stream(self.stream)
             for k in range(count):
@@ -475,6 +494,8 @@ class Ring(object):
                     self.step_slot(first + k)
             if two_streams:
                 self.stream.wait_stream(self.side)
+            if graph.ev:
+                graph.ev[1].record(self.stream)
         self.launches = before      # capture is not execution
         self._graphs[key] = graph
         return graph
@@ -499,23 +520,28 @@ class Ring(object):
         """seconds of device time for one run of `plan`, measured between two events on the launching stream; a spin
         kernel ahead of the start event absorbs the host's enqueue latency"""
         torch = self.torch
+        unit_graph, units, rem_graph, rem = plan
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(self.stream):
+            self.flush_l2()
             torch.cuda._sleep(spin_cycles)
             e0.record(self.stream)
             self.run(plan)
             e1.record(self.stream)
             self.stream.synchronize()
+        self.timed_by = "events around the graph launches"
+        if units == 0 and rem and getattr(rem_graph, "ev", None):      # one graph launch: use the events inside it
+            self.timed_by = "external events recorded inside the graph (first kernel .. last kernel)"
+            return rem_graph.ev[0].elapsed_time(rem_graph.ev[1]) / 1e3
         return e0.elapsed_time(e1) / 1e3
 
     def isolated_kernel_ns(self, spin_cycles, repeats=9):
         """one fused-step launch between two events, L2 flushed by a 256 MB fill before each: median / min in ns"""
         torch = self.torch
-        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=self.dev)
         out = []
         with torch.cuda.stream(self.stream):
             for r in range(repeats):
-                flush.fill_(r)
+                self.flush_l2()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 torch.cuda._sleep(spin_cycles)
                 e0.record(self.stream)
@@ -546,27 +572,35 @@ class Ring(object):
                 raise RuntimeError("mpe_probe_stream failed: %d" % rc)
 
         k = max(1, min(k, self.unit))
+        best = None
         with torch.cuda.stream(self.stream):
-            for i in range(self.R):
-                probe(i)
-            self.stream.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=self.stream):
-                for i in range(k):
+            for threads in (self.n_env, 2 * self.n_env, 4 * self.n_env, 8 * self.n_env):
+                threads = max(256, threads)
+                for i in range(min(self.R, 4)):
                     probe(i)
-            graph.replay()
-            self.stream.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda._sleep(spin_cycles)
-            e0.record(self.stream)
-            graph.replay()
-            e1.record(self.stream)
-            self.stream.synchronize()
-        sec = e0.elapsed_time(e1) / 1e3 / k
+                self.stream.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                ev = (torch.cuda.Event(enable_timing=True, external=True), torch.cuda.Event(enable_timing=True, external=True))
+                with torch.cuda.graph(graph, stream=self.stream):
+                    ev[0].record(self.stream)
+                    for i in range(k):
+                        probe(i)
+                    ev[1].record(self.stream)
+                graph.replay()
+                self.stream.synchronize()
+                self.flush_l2()
+                torch.cuda._sleep(spin_cycles)
+                graph.replay()
+                self.stream.synchronize()
+                sec = ev[0].elapsed_time(ev[1]) / 1e3 / k
+                if best is None or sec < best[0]:
+                    best = (sec, threads)
+        sec, threads = best
         return {"ms_per_launch": 1e3 * sec, "gbs": (rd + wr) / sec / 1e9, "launches": k, "read_bytes": rd, "write_bytes": wr,
-                "note": "pure streaming kernel (float4 loads, then dependent evict-first float4 stores), one thread per world, "
-                        "same launch path / graph replay / ring rotation: what this batch size allows a strictly "
-                        "serialized launch to reach"}
+                "threads": threads,
+                "note": "pure streaming kernel (float4 loads, then dependent evict-first float4 stores) with this config's "
+                        "read / write byte counts per launch, best of 1 / 2 / 4 / 8 threads per world, same launch path / graph "
+                        "replay / ring rotation / L2 flush: what this batch size lets ANY strictly serialized launch reach"}
 
 
 def run_b200_arm(args, rank, local_rank, world):
@@ -615,6 +649,7 @@ def run_b200_arm(args, rank, local_rank, world):
     ring.launches = 0
     t0 = time.time()
     seconds = ring.timed(plan, spin)
+    timed_by = ring.timed_by
     t1 = time.time()
     gpu_launches = ring.launches
     torch.cuda.synchronize()
@@ -705,7 +740,7 @@ def run_b200_arm(args, rank, local_rank, world):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": 1e3 * launch_s, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": "f32", "data": "synthetic", "timing": timed_by,
             "config": workload_config(args.scenario, args.scenario_kw, N_ENV, ring.n_agents, ring.bytes_per_env,
                                       ring.input_bytes_per_env, world, R),
             "agent_steps_per_sec": ring.n_agents * value,

@@ -127,7 +127,7 @@ __device__ __forceinline__ void physics(const DevDesc &d, typename P::W &w, cons
 
 // MultiAgentEnv._set_action (environment.py:144-192) for this lane's world, from the warp's staged action tiles
 // (s_act = the warp's staging base; tile i starts at Shape<P>::act_off(i))
-template <class P>
+template <class P, bool ALLOW_FORCE_DISCRETE = true>
 __device__ __forceinline__ void decode_rows(const float *s_act, int lane, const DevDesc &d, uint32_t flags,
                                             float (&ux)[P::A], float (&uy)[P::A], float *cact) {
     static_for<P::A>([&](auto ic) {
@@ -139,7 +139,7 @@ __device__ __forceinline__ void decode_rows(const float *s_act, int lane, const 
         float x = 0.0f, y = 0.0f;                                       // :145
         if constexpr (P::movable(i)) {
             float p0 = row[0], p1 = row[1], p2 = row[2], p3 = row[3], p4 = row[4];
-            if (flags & MPE_FLAG_FORCE_DISCRETE_ACTION) {               // :169-172 (first arg-max)
+            if (ALLOW_FORCE_DISCRETE && (flags & MPE_FLAG_FORCE_DISCRETE_ACTION)) {   // :169-172 (first arg-max)
                 int best = 0;
                 float bv = p0;
                 if (p1 > bv) { bv = p1; best = 1; }
@@ -225,9 +225,17 @@ __device__ __forceinline__ void pair_barrier(int id, const float (&v)[N]) {
 // dones / info and the observations of the odd agents.  It doubles the warps in flight for the same batch: batches too
 // small to fill the machine with one lane per world (world_comm at 32 768 worlds = 1.7 warps per scheduler, ~3000
 // dependent instructions each) are bound by instruction latency, not by HBM, and the observation half is most of it.
-template <class P, int MODE, bool SPLIT = false>
+//
+// HOT (fused step only): the specialisation the launcher uses whenever it can -- whole 32-world tiles, 16-byte aligned
+// action rows, float action vectors without force_discrete_action, cp.async staging.  It contains none of the cold
+// alternatives (partial-tile scalar paths, TMA staging, integer decode, arg-max), i.e. about half the static code of
+// the general kernel: with ~3 resident warps per scheduler the step is bound by each warp's own instruction stream,
+// and instruction-fetch stalls across the skipped cold blocks were ~8 % of it (profiles/).  Same arithmetic, same
+// order: bit-identical.  A ragged tail and every other flag combination run on the general kernel.
+template <class P, int MODE, bool SPLIT = false, bool HOT = false>
 __global__ void __launch_bounds__(kMaxThreads, MPE_MIN_BLOCKS) mpe_kernel(const __grid_constant__ StepArgs a) {
     static_assert(!SPLIT || MODE == kFusedStep, "warp pairs exist for the fused step only");
+    static_assert(!HOT || (MODE == kFusedStep && !SPLIT && Shape<P>::all_act_dense()), "HOT = plain fused step, dense tiles");
     constexpr int A = P::A, L = P::L, NC = Shape<P>::kNC;
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -242,8 +250,8 @@ __global__ void __launch_bounds__(kMaxThreads, MPE_MIN_BLOCKS) mpe_kernel(const 
     // grid has completed and flushed.  A warp that exits early counts as having released the dependent grid.
     if (a.flags & kFlagPdlEarly) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (w0 >= end) return;  // whole warp exits together
-    const int rows = (end - w0) < 32 ? static_cast<int>(end - w0) : 32;
-    const bool active = lane < rows;
+    const int rows = HOT ? 32 : ((end - w0) < 32 ? static_cast<int>(end - w0) : 32);
+    const bool active = HOT ? true : (lane < rows);
     const int64_t wi = w0 + (active ? lane : 0);  // inactive lanes shadow row 0 and never store
     float *s_warp = smem + warp * Shape<P>::kWarpFloats;
     uint64_t *bar = reinterpret_cast<uint64_t *>(s_warp);
@@ -259,7 +267,17 @@ __global__ void __launch_bounds__(kMaxThreads, MPE_MIN_BLOCKS) mpe_kernel(const 
     // ---- action tiles: asynchronous copies (cp.async, or TMA bulk) issued FIRST, so that they fly together
     //      with the state loads -------------------------------------------------------------------------
     bool bulk = false;
-    if constexpr ((MODE == kFusedStep || MODE == kSetAction) && Shape<P>::all_act_dense()) {
+    if constexpr (HOT) {
+        static_for<A>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            constexpr int AD = P::act_dim(i), kVec = 32 * AD / 4;
+            const float *g = a.act[i] + w0 * AD;
+            float *sdst = s_warp + Shape<P>::act_off(i);
+#pragma unroll
+            for (int q0 = 0; q0 < kVec; q0 += 32)
+                if (q0 + 32 <= kVec || q0 + lane < kVec) cp_async16(sdst + 4 * (q0 + lane), g + 4 * (q0 + lane));
+        });
+    } else if constexpr ((MODE == kFusedStep || MODE == kSetAction) && Shape<P>::all_act_dense()) {
         uintptr_t bits = 0;
 #pragma unroll
         for (int i = 0; i < A; ++i) bits |= reinterpret_cast<uintptr_t>(a.act[i]);
@@ -315,7 +333,11 @@ __global__ void __launch_bounds__(kMaxThreads, MPE_MIN_BLOCKS) mpe_kernel(const 
     float ux[A], uy[A];
     float cact[NC > 0 ? NC : 1];
     // ---- MultiAgentEnv._set_action (environment.py:144-192) --------------------------------
-    if constexpr (MODE == kFusedStep || MODE == kSetAction) {
+    if constexpr (HOT) {
+        cp_async_wait_all();
+        __syncwarp();
+        decode_rows<P, false>(s_warp, lane, d, a.flags, ux, uy, cact);
+    } else if constexpr (MODE == kFusedStep || MODE == kSetAction) {
         if (a.flags & MPE_FLAG_DISCRETE_ACTION_INPUT) {
             // env.discrete_action_input (environment.py:161-167, 185-187): act_n[i] is int32 [n_env][n_sub_i], one index
             // per sub-action (movement 0..4, then the utterance 0..dim_c-1); consecutive lanes read consecutive words
@@ -861,6 +883,7 @@ struct Program {
     bool (*validate)(const mpe_desc &);
     KernelFn fn[4];
     int smem_bytes;  // dynamic shared memory per WARP
+    KernelFn hot_fn;    // fused step specialised for whole tiles / float actions / cp.async staging (null: no such program)
     KernelFn split_fn;  // fused step with a warp PAIR per 32-world tile (small batches of heavy scenarios)
     KernelFn pipe_fn;   // software-pipelined persistent fused step (null unless every action tile is dense)
     int pipe_smem;      // dynamic shared memory per WARP of the pipelined kernel
@@ -883,6 +906,7 @@ static Program make_program() {
     p.fn[kWorldStep] = mpe_kernel<P, kWorldStep>;
     p.fn[kObserve] = mpe_kernel<P, kObserve>;
     p.split_fn = P::A >= 2 ? mpe_kernel<P, kFusedStep, true> : nullptr;
+    if constexpr (Shape<P>::all_act_dense()) p.hot_fn = mpe_kernel<P, kFusedStep, false, true>;
     p.pipe_fn = Shape<P>::all_act_dense() ? mpe_pipe_kernel<P> : nullptr;
     p.pipe_smem = Shape<P>::kPipeWarpBytes;
     p.rollout_fn = mpe_rollout_kernel<P>;
@@ -1015,6 +1039,9 @@ extern "C" int mpe_create(const mpe_desc *desc, int64_t n_env, int device, mpe_h
                                               prog->smem_bytes * max_warps_per_block(prog->smem_bytes)));
         if (prog->lanes_fn)
             CUDA_TRY(cudaFuncSetAttribute(prog->lanes_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, prog->lanes_smem * 4));
+        if (prog->hot_fn && prog->smem_bytes > 0)
+            CUDA_TRY(cudaFuncSetAttribute(prog->hot_fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          prog->smem_bytes * max_warps_per_block(prog->smem_bytes)));
         if (prog->pipe_fn)
             CUDA_TRY(cudaFuncSetAttribute(prog->pipe_fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           prog->pipe_smem * max_warps_per_block(prog->pipe_smem)));
@@ -1211,50 +1238,72 @@ static int launch(mpe_handle h, int mode, StepArgs &args, void *stream, int64_t 
         }
     }
     int64_t warps = (args.count + 31) / 32;
-    // Warp pairs (see mpe_kernel<..., SPLIT>): MPE_B200_SPLIT = 0 never, 1 always, unset: when one warp per tile leaves
-    // the machine under ~2.5 warps per scheduler AND the scenario is heavy enough (>= 4 agents) for instruction
-    // latency rather than HBM to bound the step -- thresholds from measurements, see profiles/
+    // Warp pairs (see mpe_kernel<..., SPLIT>): MPE_B200_SPLIT = 1 always, 2 = for small batches of >= 4-agent scenarios,
+    // unset / 0 never.  MEASURED SLOWER than one warp per tile at every size but 8192 worlds (profiles/r2a_sweep_split*:
+    // world_comm 32768 worlds 15.2 vs 11.2 us, spread 65536 worlds 9.8 vs 5.8 us): the duplicated physics + reward cost
+    // more than the extra warps hide.  Kept as an opt-in, bit-identical alternative.
     static const int split_env = [] { const char *e = getenv("MPE_B200_SPLIT"); return e ? atoi(e) : -1; }();
     static const int64_t split_max_warps = [] { const char *e = getenv("MPE_B200_SPLIT_MAX_WARPS"); return e ? atoll(e) : 148LL * 10; }();
     const bool split = mode == kFusedStep && h->prog->split_fn != nullptr &&
-                       (split_env == 1 || (split_env < 0 && h->prog->A >= 4 && warps <= split_max_warps));
+                       (split_env == 1 || (split_env == 2 && h->prog->A >= 4 && warps <= split_max_warps));
     if (split) warps *= 2;
-    // Warps are autonomous, so the block size only sets scheduling granularity (measured at 65536 worlds:
-    // 1 / 2 / 4 warps per block = 6.69 / 6.34 / 7.06 us per step): tiny batches use one warp per block so
-    // that the few blocks spread over all 148 SMs, mid-size batches two, large ones four.
     static const int wpb_env = [] { const char *e = getenv("MPE_B200_WPB"); int v = e ? atoi(e) : 0; return (v >= 1 && v <= kMaxWarpsPerBlock) ? v : 0; }();
-    int wpb = wpb_env ? wpb_env : (warps <= 148 * 4 ? 1 : (warps <= 148 * 64 ? 2 : 4));
-    if (wpb > max_warps_per_block(h->prog->smem_bytes)) wpb = max_warps_per_block(h->prog->smem_bytes);
-    if (split) wpb = (wpb < 2) ? 2 : (wpb & ~1);      // a pair lives in one block
-    const int64_t blocks = (warps + wpb - 1) / wpb;
-    if (blocks > 0x7fffffffLL) return MPE_ERR_BAD_ARG;
+    // action tiles: cp.async (LDGSTS) by default -- measured 1-5 % faster than the TMA bulk copy + mbarrier at every
+    // batch size (no barrier init / proxy fence in the prologue); MPE_B200_ACT_STAGING=tma selects the TMA path
+    static const bool cpasync = [] { const char *e = getenv("MPE_B200_ACT_STAGING"); return !(e && e[0] == 't'); }();
+    static const bool hot_env = [] { const char *e = getenv("MPE_B200_HOT"); return !(e && e[0] == '0'); }();   // 0 = general kernel only
     int prev = 0;
     CUDA_TRY(cudaGetDevice(&prev));
     if (prev != h->device) CUDA_TRY(cudaSetDevice(h->device));
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(static_cast<unsigned>(blocks));
-    cfg.blockDim = dim3(32 * wpb);
-    cfg.dynamicSmemBytes = static_cast<size_t>(h->prog->smem_bytes) * wpb;
-    cfg.stream = static_cast<cudaStream_t>(stream);
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl_mode() ? 1 : 0;
     if (pdl_mode() == 2) args.flags |= kFlagPdlEarly;
     if (pdl_mode() == 3) args.flags |= kFlagPdlAfterLoads;
     if (pdl_mode() == 4) args.flags |= kFlagPdlAtExit;
     if (pdl_mode() == 5) args.flags |= kFlagPdlAfterIssue;
-    // action tiles: cp.async (LDGSTS) by default -- measured 1-5 % faster than the TMA bulk copy + mbarrier at every
-    // batch size (no barrier init / proxy fence in the prologue); MPE_B200_ACT_STAGING=tma selects the TMA path
-    static const bool cpasync = [] { const char *e = getenv("MPE_B200_ACT_STAGING"); return !(e && e[0] == 't'); }();
     if (cpasync) args.flags |= kFlagCpAsync;
-    void *params[] = {&args};
-    cudaError_t e = cudaLaunchKernelExC(&cfg, reinterpret_cast<const void *>(split ? h->prog->split_fn : h->prog->fn[mode]), params);
+    // one grid of autonomous warps over [sa.begin, sa.begin + sa.count)
+    auto launch_grid = [&](KernelFn fn, StepArgs &sa, bool pairs) -> int {
+        int64_t nw = (sa.count + 31) / 32;
+        if (pairs) nw *= 2;
+        // Warps are autonomous, so the block size only sets scheduling granularity (measured at 65536 worlds:
+        // 1 / 2 / 4 warps per block = 6.69 / 6.34 / 7.06 us per step): tiny batches use one warp per block so
+        // that the few blocks spread over all 148 SMs, mid-size batches two, large ones four.
+        int wpb = wpb_env ? wpb_env : (nw <= 148 * 4 ? 1 : (nw <= 148 * 64 ? 2 : 4));
+        if (wpb > max_warps_per_block(h->prog->smem_bytes)) wpb = max_warps_per_block(h->prog->smem_bytes);
+        if (pairs) wpb = (wpb < 2) ? 2 : (wpb & ~1);      // a pair lives in one block
+        const int64_t blocks = (nw + wpb - 1) / wpb;
+        if (blocks > 0x7fffffffLL) return MPE_ERR_BAD_ARG;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(static_cast<unsigned>(blocks));
+        cfg.blockDim = dim3(32 * wpb);
+        cfg.dynamicSmemBytes = static_cast<size_t>(h->prog->smem_bytes) * wpb;
+        cfg.stream = static_cast<cudaStream_t>(stream);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = pdl_mode() ? 1 : 0;
+        void *params[] = {&sa};
+        cudaError_t e = cudaLaunchKernelExC(&cfg, reinterpret_cast<const void *>(fn), params);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelExC");
+        __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED);
+        return MPE_OK;
+    };
+    int rc = MPE_OK;
+    // the specialised fused step (mpe_kernel<..., HOT>) takes every whole tile it is eligible for
+    bool hot = hot_env && cpasync && !split && mode == kFusedStep && h->prog->hot_fn != nullptr && args.count >= 32 &&
+               !(args.flags & (MPE_FLAG_DISCRETE_ACTION_INPUT | MPE_FLAG_FORCE_DISCRETE_ACTION));
+    for (int i = 0; hot && i < h->prog->A; ++i)
+        hot = ((reinterpret_cast<uintptr_t>(args.act[i]) + static_cast<uintptr_t>(args.begin) * h->prog->act_dim[i] * 4) & 15u) == 0;
+    if (hot) {
+        StepArgs ha = args;
+        ha.count = args.count / 32 * 32;
+        rc = launch_grid(h->prog->hot_fn, ha, false);
+        args.begin += ha.count;
+        args.count -= ha.count;
+    }
+    if (rc == MPE_OK && args.count > 0) rc = launch_grid(split ? h->prog->split_fn : h->prog->fn[mode], args, split);
     if (prev != h->device) cudaSetDevice(prev);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelExC");
-    __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED);
-    return MPE_OK;
+    return rc;
 }
 
 static bool ok16(const void *p) { return p != nullptr && (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

@@ -266,8 +266,8 @@ def test_bench_reference_arm_contract():
     assert r["steps_timed_per_process"] == 6000 and cb["warmup_per_process"] >= 100
     # the arm never loads CUDA or the product library: only the CPU oracle (its own infrastructure)
     assert r["native_so_in_process"] == ["oracle/_build/libmpe_oracle.so"], r["native_so_in_process"]
-    # same config dict as the GPU arm builds for this workload (ring sized on input bytes: 132 B x 65536 x 31 > 2 x L2)
-    assert r["config"]["ring_batches"] == 31 and r["config"]["bytes_per_env_step"] == 411
+    # same config dict as the GPU arm builds for this workload (ring sized on input bytes: 132 B x 65536 x 123 > 8 x L2)
+    assert r["config"]["ring_batches"] == 123 and r["config"]["bytes_per_env_step"] == 411
     # under torchrun every rank but 0 exits silently
     env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
@@ -286,5 +286,6 @@ def test_bench_shape_formula_equals_library(tag):
     act, obs, bpe, ibpe = bench.shapes_from_oracle(w.descriptor())
     sh = w.native_shapes()
     assert act == sh.act_dims and obs == sh.obs_dims and bpe == sh.bytes_per_env_step
-    assert 0 < ibpe < bpe and bench.ring_size(ibpe, 65536) * ibpe * 65536 > 2 * bench.L2_BYTES
-    assert bench.ring_size(ibpe, 1 << 22) == 3
+    R = bench.ring_size(ibpe, 65536)
+    assert 0 < ibpe < bpe and (R == bench.MAX_RING or R * ibpe * 65536 > bench.L2_MULTIPLE * bench.L2_BYTES)
+    assert bench.ring_size(ibpe, 1 << 26) == 3      # huge batches: the minimum ring
