@@ -375,13 +375,20 @@ np.savez(sys.argv[1], **out)
 """
 
 
-@pytest.mark.parametrize("variant", ["MPE_B200_SPLIT", "MPE_B200_PIPE"])
+ALT_KERNELS = {
+    "general_kernel_instead_of_hot": {"MPE_B200_HOT": "0"},     # the un-specialised fused step for every tile
+    "warp_pair_split": {"MPE_B200_SPLIT": "1"},
+    "software_pipelined_persistent": {"MPE_B200_PIPE": "1"},
+}
+
+
+@pytest.mark.parametrize("variant", list(ALT_KERNELS))
 def test_alternative_step_kernels_are_bit_identical(tmp_path, variant):
-    """MPE_B200_SPLIT=1 runs every fused step with a warp PAIR per 32-world tile (both warps do the physics, each
-    writes half of the outputs; the in-place state update is ordered by a pair barrier).  MPE_B200_PIPE=1 runs the
-    software-pipelined persistent kernel (all inputs of the next tile prefetched with cp.async; ragged tails go to the
-    regular kernel).  Three consecutive steps of eight scenarios with ragged batch sizes must equal the default
-    one-warp-per-tile kernel bit for bit."""
+    """The default fused step runs whole tiles on the HOT specialisation and ragged tails on the general kernel.
+    MPE_B200_HOT=0 runs everything on the general kernel; MPE_B200_SPLIT=1 uses a warp PAIR per 32-world tile (both
+    warps do the physics, each writes half of the outputs; the in-place state update is ordered by a pair barrier);
+    MPE_B200_PIPE=1 runs the software-pipelined persistent kernel (all inputs of the next tile prefetched with
+    cp.async).  Three consecutive steps of eight scenarios with ragged batch sizes must agree bit for bit."""
     import os
     import subprocess
     import sys
@@ -390,12 +397,10 @@ def test_alternative_step_kernels_are_bit_identical(tmp_path, variant):
     for mode in ("0", "1"):
         path = str(tmp_path / ("alt%s.npz" % mode))
         env = dict(os.environ)
-        env.pop("MPE_B200_SPLIT", None)
-        env.pop("MPE_B200_PIPE", None)
+        for k in ("MPE_B200_SPLIT", "MPE_B200_PIPE", "MPE_B200_HOT"):
+            env.pop(k, None)
         if mode == "1":
-            env[variant] = "1"
-        else:
-            env["MPE_B200_SPLIT"] = "0"      # the reference run: plain one-warp-per-tile kernel at every size
+            env.update(ALT_KERNELS[variant])
         subprocess.run([sys.executable, "-c", _SPLIT_SCRIPT % {"root": root}, path], check=True, env=env, timeout=900)
         res[mode] = dict(np.load(path))
     assert set(res["0"]) == set(res["1"]) and len(res["0"]) >= 40
