@@ -207,6 +207,9 @@ __device__ __forceinline__ void write_observations(const StepArgs &a, const DevD
     }
 }
 
+#ifndef MPE_BOUND_THREADS
+#define MPE_BOUND_THREADS kMaxThreads   // register-budget experiments: -DMPE_BOUND_THREADS=128 lifts the cap from 128 to 255
+#endif
 #ifndef MPE_MIN_BLOCKS
 #define MPE_MIN_BLOCKS 1   // 512-thread bound x 1 block = the same 128-register budget that measured best
 #endif
@@ -233,7 +236,7 @@ __device__ __forceinline__ void pair_barrier(int id, const float (&v)[N]) {
 // and instruction-fetch stalls across the skipped cold blocks were ~8 % of it (profiles/).  Same arithmetic, same
 // order: bit-identical.  A ragged tail and every other flag combination run on the general kernel.
 template <class P, int MODE, bool SPLIT = false, bool HOT = false>
-__global__ void __launch_bounds__(kMaxThreads, MPE_MIN_BLOCKS) mpe_kernel(const __grid_constant__ StepArgs a) {
+__global__ void __launch_bounds__(MPE_BOUND_THREADS, MPE_MIN_BLOCKS) mpe_kernel(const __grid_constant__ StepArgs a) {
     static_assert(!SPLIT || MODE == kFusedStep, "warp pairs exist for the fused step only");
     static_assert(!HOT || (MODE == kFusedStep && !SPLIT && Shape<P>::all_act_dense()), "HOT = plain fused step, dense tiles");
     constexpr int A = P::A, L = P::L, NC = Shape<P>::kNC;
@@ -455,7 +458,7 @@ __global__ void __launch_bounds__(kMaxThreads, MPE_MIN_BLOCKS) mpe_kernel(const 
 // of different tiles overlap inside one strictly ordered launch.  Same arithmetic functions as mpe_kernel: results
 // are bit-identical (tests/test_gpu_parity.py).  Full tiles only; the launcher sends a ragged tail to mpe_kernel.
 template <class P>
-__global__ void __launch_bounds__(kMaxThreads, MPE_MIN_BLOCKS) mpe_pipe_kernel(const __grid_constant__ StepArgs a) {
+__global__ void __launch_bounds__(MPE_BOUND_THREADS, MPE_MIN_BLOCKS) mpe_pipe_kernel(const __grid_constant__ StepArgs a) {
     constexpr int A = P::A, L = P::L, NC = Shape<P>::kNC;
     using S = Shape<P>;
     extern __shared__ __align__(16) float smem[];
@@ -577,7 +580,7 @@ struct RolloutArgs {
 };
 
 template <class P>
-__global__ void __launch_bounds__(kMaxThreads, MPE_MIN_BLOCKS) mpe_rollout_kernel(const __grid_constant__ RolloutArgs ra) {
+__global__ void __launch_bounds__(MPE_BOUND_THREADS, MPE_MIN_BLOCKS) mpe_rollout_kernel(const __grid_constant__ RolloutArgs ra) {
     constexpr int A = P::A, L = P::L, NC = Shape<P>::kNC;
     const StepArgs &a = ra.s;
     extern __shared__ __align__(16) float smem[];
