@@ -465,6 +465,23 @@ class Ring(object):
         sweep would leave 126 MB of dirty lines whose write-back competes with the timed steps)"""
         self._flush.sum()
 
+    def warm_tlb(self):
+        """touch one 4-byte word per 32 KB of every ring tensor (state, actions, outputs): address translations are
+        resident as they are for a trainer that reuses its buffers every step, while the L2 stays cold (the touches
+        bring in one 32-byte sector per 32 KB, ~0.1 % of the data).  MPE_BENCH_TLB_WARM=0 disables it."""
+        if os.environ.get("MPE_BENCH_TLB_WARM", "1") == "0":
+            return
+        torch = self.torch
+        acc = None
+        for env, nw, acts, ptrs, flags in self.slots:
+            for t in [nw.agent_pv, nw.lm_p, nw.comm, nw.out.slab] + list(acts):
+                v = t.view(-1)
+                if v.dtype != torch.float32:
+                    v = v.view(torch.uint8)[: v.numel() // 4 * 4].view(torch.float32) if v.dtype == torch.uint8 else v.float()
+                part = v[:: 8192].sum()
+                acc = part if acc is None else acc + part
+        self._tlb_sink = acc
+
     def _capture(self, first, count, two_streams, lead=0):
         """one CUDA graph stepping slots first .. first+count-1 (mod R), strictly in order on one stream, or with
         even / odd positions on two streams (fork / join) for the two-batches-in-flight extra.  The graph records an
@@ -531,6 +548,7 @@ class Ring(object):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(self.stream):
             self.flush_l2()
+            self.warm_tlb()
             torch.cuda._sleep(spin_cycles)
             e0.record(self.stream)
             self.run(plan)

@@ -125,6 +125,88 @@ __device__ __forceinline__ void physics(const DevDesc &d, typename P::W &w, cons
 }
 
 
+// ---- warp-pair physics (SPLIT) ------------------------------------------------------------------------------------
+// The active (colliding) pairs of apply_environment_force, numbered in the reference's (a, b) order.
+template <class P>
+__host__ __device__ constexpr bool pair_active(int a, int b) {
+    return b > a && P::agent_collides(a) && (b < P::A ? P::agent_collides(b) : P::landmark_collides(b - P::A));
+}
+template <class P>
+__host__ __device__ constexpr int pair_index(int a, int b) {   // number of active pairs before (a, b)
+    int k = 0;
+    for (int aa = 0; aa < P::A; ++aa)
+        for (int bb = aa + 1; bb < P::A + P::L; ++bb) {
+            if (aa == a && bb == b) return k;
+            if (pair_active<P>(aa, bb)) ++k;
+        }
+    return k;
+}
+template <class P>
+__host__ __device__ constexpr int pair_count() { return pair_index<P>(P::A, P::A + P::L); }
+
+__device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+// Same result as physics<P>, bit for bit, computed by TWO warps that hold the same 32 worlds: warp `half` evaluates the
+// contact forces of the pairs with index % 2 == half (the MUFU-heavy part) and publishes them in the pair's exchange
+// buffer `ex` ([pair][lane] float2); after the pair barrier both warps read ALL pair forces back and accumulate them in
+// the reference's order, then integrate.  The barrier also orders the partner's state loads before the in-place store.
+template <class P>
+__device__ __forceinline__ void physics_split(const DevDesc &d, typename P::W &w, const float (&ux)[P::A],
+                                              const float (&uy)[P::A], int half, float2 *ex, int lane, int bar_id) {
+    constexpr int A = P::A, L = P::L;
+    const float k = d.contact_margin, cf = d.contact_force;
+    static_for<A>([&](auto ac) {
+        static_for<A + L>([&](auto bc) {
+            constexpr int a = decltype(ac)::value, b = decltype(bc)::value;
+            if constexpr (pair_active<P>(a, b)) {
+                constexpr int idx = pair_index<P>(a, b);
+                if ((idx & 1) == half) {   // warp-uniform
+                    constexpr bool b_agent = b < A;
+                    constexpr int bi = b_agent ? b : 0, bl = b_agent ? 0 : b - A;
+                    const float bx = b_agent ? w.px[bi] : w.lx[bl];
+                    const float by = b_agent ? w.py[bi] : w.ly[bl];
+                    const float sb = b_agent ? d.a_size[bi] : d.l_size[bl];
+                    ex[idx * 32 + lane] = pair_force(__fsub_rn(w.px[a], bx), __fsub_rn(w.py[a], by),
+                                                     __fadd_rn(d.a_size[a], sb), cf, k, d.inv_margin);
+                }
+            }
+        });
+    });
+    pair_sync(bar_id);
+    float fx[A], fy[A];
+#pragma unroll
+    for (int i = 0; i < A; ++i) {  // apply_action_force (core.py:134-140)
+        fx[i] = ux[i];
+        fy[i] = uy[i];
+    }
+    static_for<A>([&](auto ac) {
+        static_for<A + L>([&](auto bc) {
+            constexpr int a = decltype(ac)::value, b = decltype(bc)::value;
+            if constexpr (pair_active<P>(a, b)) {
+                constexpr int idx = pair_index<P>(a, b);
+                const float2 f = ex[idx * 32 + lane];
+                if (P::movable(a)) {
+                    fx[a] = __fadd_rn(fx[a], f.x);
+                    fy[a] = __fadd_rn(fy[a], f.y);
+                }
+                if constexpr (b < A) {
+                    if (P::movable(b)) {
+                        fx[b] = __fsub_rn(fx[b], f.x);
+                        fy[b] = __fsub_rn(fy[b], f.y);
+                    }
+                }
+            }
+        });
+    });
+#pragma unroll
+    for (int i = 0; i < A; ++i) {
+        if (!P::movable(i)) continue;
+        const float4 r = integrate_entity<P::kSpeedLimit>(w.px[i], w.py[i], w.vx[i], w.vy[i], fx[i], fy[i], d.keep,
+                                                          d.a_dt_over_mass[i], d.dt, d.a_max_speed[i]);
+        w.px[i] = r.x; w.py[i] = r.y; w.vx[i] = r.z; w.vy[i] = r.w;
+    }
+}
+
 // MultiAgentEnv._set_action (environment.py:144-192) for this lane's world, from the warp's staged action tiles
 // (s_act = the warp's staging base; tile i starts at Shape<P>::act_off(i))
 template <class P, bool ALLOW_FORCE_DISCRETE = true>
@@ -168,7 +250,12 @@ __device__ __forceinline__ void decode_rows(const float *s_act, int lane, const 
 
 // observation rows of one 32-world tile: full warps write through the warp-private tiles and stream them out as
 // coalesced 16-byte stores; the batch's last, partial warp writes its rows straight to global memory.
-// `half` < 0: every agent; 0 / 1: only the even / odd agents (warp pairs).
+// `half` < 0: every agent; 0: agents [0, split_point); 1: agents [split_point, A) (warp pairs; the second warp also
+// computes the rewards, so it gets the smaller share: split_point = ceil(2A/3)).
+template <class P>
+__host__ __device__ constexpr int split_point() { return (2 * P::A + 2) / 3; }
+template <class P>
+__host__ __device__ constexpr int agent_half(int i) { return i < split_point<P>() ? 0 : 1; }
 template <class P>
 __device__ __forceinline__ void write_observations(const StepArgs &a, const DevDesc &d, const typename P::W &w, float *s_warp,
                                                    int lane, int rows, bool active, int64_t w0, int64_t wi, int half) {
@@ -181,7 +268,7 @@ __device__ __forceinline__ void write_observations(const StepArgs &a, const DevD
         static_for<A>([&](auto ic) {
             constexpr int i = decltype(ic)::value;
             constexpr int OD = P::obs_dim(i);
-            if (half >= 0 && (i & 1) != half) return;     // warp-uniform: the partner warp writes this agent
+            if (half >= 0 && agent_half<P>(i) != half) return;     // warp-uniform: the partner warp writes this agent
             TileWriter<OD> o(s_warp + Shape<P>::obs_off(i), lane);
             P::template observe<i>(d, w, o);
             if constexpr (!Shape<P>::obs_dense(i)) {  // padded tiles share one slot
@@ -194,13 +281,13 @@ __device__ __forceinline__ void write_observations(const StepArgs &a, const DevD
         static_for<A>([&](auto ic) {
             constexpr int i = decltype(ic)::value;
             constexpr int OD = P::obs_dim(i);
-            if (half >= 0 && (i & 1) != half) return;
+            if (half >= 0 && agent_half<P>(i) != half) return;
             if constexpr (Shape<P>::obs_dense(i)) obs_tile_store<OD>(a.obs[i] + w0 * OD, s_warp + Shape<P>::obs_off(i), lane);
         });
     } else if (active) {  // the batch's last, partial warp: rows go straight to global memory
         static_for<A>([&](auto ic) {
             constexpr int i = decltype(ic)::value;
-            if (half >= 0 && (i & 1) != half) return;
+            if (half >= 0 && agent_half<P>(i) != half) return;
             RowWriter o{a.obs[i] + wi * P::obs_dim(i)};
             P::template observe<i>(d, w, o);
         });
@@ -214,20 +301,12 @@ __device__ __forceinline__ void write_observations(const StepArgs &a, const DevD
 #define MPE_MIN_BLOCKS 1   // 512-thread bound x 1 block = the same 128-register budget that measured best
 #endif
 
-// bar.sync among the 64 threads of a warp pair; the float operands make the barrier wait for the loads that
-// produced them (one component per LDG.128 suffices: the four components of a float4 arrive together)
-template <int N>
-__device__ __forceinline__ void pair_barrier(int id, const float (&v)[N]) {
-    static_assert(N <= 8, "at most 8 agents");
-    asm volatile("bar.sync %0, 64;" ::"r"(id), "f"(v[0]), "f"(v[N > 1 ? 1 : 0]), "f"(v[N > 2 ? 2 : 0]), "f"(v[N > 3 ? 3 : 0]),
-                 "f"(v[N > 4 ? 4 : 0]), "f"(v[N > 5 ? 5 : 0]), "f"(v[N > 6 ? 6 : 0]), "f"(v[N > 7 ? 7 : 0]) : "memory");
-}
-
-// SPLIT (fused step only): TWO warps share a 32-world tile.  Both load the state and the actions and run the physics
-// (bit-identical results); warp 2k writes the new state and the observations of the even agents, warp 2k+1 the rewards /
-// dones / info and the observations of the odd agents.  It doubles the warps in flight for the same batch: batches too
-// small to fill the machine with one lane per world (world_comm at 32 768 worlds = 1.7 warps per scheduler, ~3000
-// dependent instructions each) are bound by instruction latency, not by HBM, and the observation half is most of it.
+// SPLIT (fused step only): TWO warps share a 32-world tile.  Both load the state and the actions; each evaluates half
+// of the contact forces (exchanged through shared memory, accumulated by both in the reference's order: bit-identical
+// state); warp 2k writes the new state and the observations of the first ceil(2A/3) agents, warp 2k+1 computes and
+// writes the rewards / dones / info and the remaining observations.  It doubles the warps in flight and nearly halves
+// each warp's instruction stream: batches too small to fill the machine with one lane per world (world_comm at 32 768
+// worlds = 1.7 warps per scheduler, ~2500 dependent instructions each) are bound by instruction latency, not by HBM.
 //
 // HOT (fused step only): the specialisation the launcher uses whenever it can -- whole 32-world tiles, 16-byte aligned
 // action rows, float action vectors without force_discrete_action, cp.async staging.  It contains none of the cold
@@ -239,6 +318,7 @@ template <class P, int MODE, bool SPLIT = false, bool HOT = false>
 __global__ void __launch_bounds__(MPE_BOUND_THREADS, MPE_MIN_BLOCKS) mpe_kernel(const __grid_constant__ StepArgs a) {
     static_assert(!SPLIT || MODE == kFusedStep, "warp pairs exist for the fused step only");
     static_assert(!HOT || (MODE == kFusedStep && !SPLIT && Shape<P>::all_act_dense()), "HOT = plain fused step, dense tiles");
+    static_assert(!SPLIT || pair_count<P>() * 64 <= Shape<P>::kWarpFloats - Shape<P>::obs_base(), "pair exchange must fit the obs tiles");
     constexpr int A = P::A, L = P::L, NC = Shape<P>::kNC;
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -407,9 +487,14 @@ __global__ void __launch_bounds__(MPE_BOUND_THREADS, MPE_MIN_BLOCKS) mpe_kernel(
     if (a.flags & kFlagPdlAfterLoads) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // ---- World.step (core.py:117-131) --------------------------------------------------------
     if constexpr (MODE == kFusedStep || MODE == kWorldStep) {
-        // the partner warp must have received the old state before this warp overwrites it in place
-        if constexpr (SPLIT) pair_barrier(1 + (warp >> 1), w.px);
-        physics<P>(d, w, ux, uy);
+        if constexpr (SPLIT) {
+            // exchange buffer = the observation-tile area of the pair's even warp (idle until the observations are
+            // written; the second barrier below keeps it intact until the partner has read every pair force)
+            float2 *ex = reinterpret_cast<float2 *>(smem + (warp & ~1) * Shape<P>::kWarpFloats + Shape<P>::obs_base());
+            physics_split<P>(d, w, ux, uy, half, ex, lane, 1 + (warp >> 1));
+        } else {
+            physics<P>(d, w, ux, uy);
+        }
 #pragma unroll
         for (int q = 0; q < NC; ++q) w.c[q] = cact[q];  // update_agent_state (core.py:171-177)
         if (active && half == 0) {
@@ -426,14 +511,17 @@ __global__ void __launch_bounds__(MPE_BOUND_THREADS, MPE_MIN_BLOCKS) mpe_kernel(
     float rew[A];
     float info[(P::INFO > 0 ? P::INFO : 1) * A];
     P::prepare(d, w);   // per-world predicates shared by all agents' observations (world_comm: forest membership)
-    P::reward(d, w, rew, (P::INFO > 0 && a.info != nullptr) ? info : nullptr);
-    if (a.flags & MPE_FLAG_SHARED_REWARD) {                                  // :100-102 np.sum(reward_n)
-        float s = 0.0f;
+    if (!SPLIT || half == 1) {   // warp pairs: only the warp that stores the rewards computes them
+        P::reward(d, w, rew, (P::INFO > 0 && a.info != nullptr) ? info : nullptr);
+        if (a.flags & MPE_FLAG_SHARED_REWARD) {                                  // :100-102 np.sum(reward_n)
+            float s = 0.0f;
 #pragma unroll
-        for (int i = 0; i < A; ++i) s += rew[i];
+            for (int i = 0; i < A; ++i) s += rew[i];
 #pragma unroll
-        for (int i = 0; i < A; ++i) rew[i] = s;
+            for (int i = 0; i < A; ++i) rew[i] = s;
+        }
     }
+    if constexpr (SPLIT) pair_sync(1 + (warp >> 1));   // the partner has consumed the exchange buffer (= obs tiles of the even warp)
     if (!(a.flags & (kFlagPdlEarly | kFlagPdlAfterLoads | kFlagPdlAtExit | kFlagPdlAfterIssue))) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     write_observations<P>(a, d, w, s_warp, lane, rows, active, w0, wi, SPLIT ? half : -1);
     if (active && (!SPLIT || half == 1)) {
@@ -908,7 +996,8 @@ static Program make_program() {
     p.fn[kSetAction] = mpe_kernel<P, kSetAction>;
     p.fn[kWorldStep] = mpe_kernel<P, kWorldStep>;
     p.fn[kObserve] = mpe_kernel<P, kObserve>;
-    p.split_fn = P::A >= 2 ? mpe_kernel<P, kFusedStep, true> : nullptr;
+    if constexpr (P::A >= 2 && pair_count<P>() * 64 <= Shape<P>::kWarpFloats - Shape<P>::obs_base())
+        p.split_fn = mpe_kernel<P, kFusedStep, true>;     // (the pair exchange must fit the observation tiles)
     if constexpr (Shape<P>::all_act_dense()) p.hot_fn = mpe_kernel<P, kFusedStep, false, true>;
     p.pipe_fn = Shape<P>::all_act_dense() ? mpe_pipe_kernel<P> : nullptr;
     p.pipe_smem = Shape<P>::kPipeWarpBytes;
