@@ -101,7 +101,9 @@ def workload_config(scenario, kw, n_env, n_agents, bytes_per_env, input_bytes_pe
             "bytes_per_env_step": bytes_per_env, "input_bytes_per_env_step": input_bytes_per_env,
             "l2_policy": "inputs larger than L2 AND L2 flushed: steps rotate over %d independent batches; their INPUTS alone "
                          "(state + actions, %.1f MB per batch) total %.0f MB %s %d x 126 MB L2 (all bytes %.0f MB), and a "
-                         "512 MB read-only sweep evicts the L2 right before every timed region"
+                         "512 MB read-only sweep evicts the L2 right before every timed region; address translations are "
+                         "then re-warmed by touching one word per 32 KB of the ring (a trainer reuses its buffers; cold-TLB "
+                         "first touches cost 0.5 us per step at K = 20, profiles/r2d_*)"
                          % (ring, input_bytes_per_env * n_env / 1e6, ring * input_bytes_per_env * n_env / 1e6,
                             ">=" if ring * input_bytes_per_env * n_env >= L2_MULTIPLE * L2_BYTES else "(ring capped) <",
                             L2_MULTIPLE, ring * bytes_per_env * n_env / 1e6),
@@ -617,6 +619,8 @@ class Ring(object):
                 graph.replay()
                 self.stream.synchronize()
                 self.flush_l2()
+                if os.environ.get("MPE_BENCH_TLB_WARM", "1") != "0":      # same treatment as the ring (warm_tlb)
+                    self._tlb_sink = src[::8192].sum() + dst[::8192].sum()
                 torch.cuda._sleep(spin_cycles)
                 graph.replay()
                 self.stream.synchronize()
@@ -647,6 +651,8 @@ class Ring(object):
             graph.replay()
             self.stream.synchronize()
             self.flush_l2()
+            if os.environ.get("MPE_BENCH_TLB_WARM", "1") != "0":
+                self._tlb_sink = csrc[::8192].sum() + cdst[::8192].sum()
             torch.cuda._sleep(spin_cycles)
             graph.replay()
             self.stream.synchronize()
