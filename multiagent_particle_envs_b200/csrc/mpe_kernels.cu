@@ -46,18 +46,25 @@ struct Shape {
         return ((od / unit) | 1) * unit;
     }
     __host__ __device__ static constexpr bool obs_dense(int i) { return obs_pitch(i) == P::obs_dim(i); }
+    // a tile with a slot of its own is written by its agent's observe() and streamed out later together with the others;
+    // tiles without one share a slot (write, sync, stream, sync).  -DMPE_COMPACT_OBS=1 (A/B builds): every tile shares,
+    // which shrinks the staging of spread N=3 from 8.8 to 4.3 KB per warp (more blocks of the NEXT grid fit beside this one)
+#ifndef MPE_COMPACT_OBS
+#define MPE_COMPACT_OBS 0
+#endif
+    __host__ __device__ static constexpr bool obs_private(int i) { return obs_dense(i) && !MPE_COMPACT_OBS; }
     __host__ __device__ static constexpr int obs_floats(int i) { return (32 * obs_pitch(i) + 3) & ~3; }
     __host__ __device__ static constexpr int obs_base() { return act_off(P::A); }
-    __host__ __device__ static constexpr int shared_obs_floats() { int m = 0; for (int i = 0; i < P::A; ++i) if (!obs_dense(i)) m = obs_floats(i) > m ? obs_floats(i) : m; return m; }
+    __host__ __device__ static constexpr int shared_obs_floats() { int m = 0; for (int i = 0; i < P::A; ++i) if (!obs_private(i)) m = obs_floats(i) > m ? obs_floats(i) : m; return m; }
     __host__ __device__ static constexpr int obs_off(int i) {
-        if (!obs_dense(i)) return obs_base();
+        if (!obs_private(i)) return obs_base();
         int s = obs_base() + shared_obs_floats();
-        for (int j = 0; j < i; ++j) if (obs_dense(j)) s += obs_floats(j);
+        for (int j = 0; j < i; ++j) if (obs_private(j)) s += obs_floats(j);
         return s;
     }
     __host__ __device__ static constexpr int warp_floats() {
         int s = obs_base() + shared_obs_floats();
-        for (int j = 0; j < P::A; ++j) if (obs_dense(j)) s += obs_floats(j);
+        for (int j = 0; j < P::A; ++j) if (obs_private(j)) s += obs_floats(j);
         return (s + 3) & ~3;
     }
     static constexpr int kWarpFloats = warp_floats();
@@ -271,7 +278,7 @@ __device__ __forceinline__ void write_observations(const StepArgs &a, const DevD
             if (half >= 0 && agent_half<P>(i) != half) return;     // warp-uniform: the partner warp writes this agent
             TileWriter<OD> o(s_warp + Shape<P>::obs_off(i), lane);
             P::template observe<i>(d, w, o);
-            if constexpr (!Shape<P>::obs_dense(i)) {  // padded tiles share one slot
+            if constexpr (!Shape<P>::obs_private(i)) {  // tiles without a slot of their own share one
                 __syncwarp();
                 obs_tile_store<OD>(a.obs[i] + w0 * OD, s_warp + Shape<P>::obs_off(i), lane);
                 __syncwarp();
@@ -282,7 +289,7 @@ __device__ __forceinline__ void write_observations(const StepArgs &a, const DevD
             constexpr int i = decltype(ic)::value;
             constexpr int OD = P::obs_dim(i);
             if (half >= 0 && agent_half<P>(i) != half) return;
-            if constexpr (Shape<P>::obs_dense(i)) obs_tile_store<OD>(a.obs[i] + w0 * OD, s_warp + Shape<P>::obs_off(i), lane);
+            if constexpr (Shape<P>::obs_private(i)) obs_tile_store<OD>(a.obs[i] + w0 * OD, s_warp + Shape<P>::obs_off(i), lane);
         });
     } else if (active) {  // the batch's last, partial warp: rows go straight to global memory
         static_for<A>([&](auto ic) {
