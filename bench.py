@@ -762,7 +762,12 @@ def run_b200_arm(args, rank, local_rank, world):
         return tot / mx, mx, nbytes, chk
 
     e2e_value, e2e_max, d2h, checksum = e2e_run(env, True)
+    # the fresh-array semantics copy 15 MB per step on the host: give torch's CPU copy the threads a user process would
+    # have (this script pins OMP to 1 thread for the one-world-per-process CPU arm)
+    host_threads = max(1, min(16, len(os.sched_getaffinity(0)) // max(world, 1)))
+    torch.set_num_threads(host_threads)
     fresh_value, fresh_max, _, _ = e2e_run(env, False)
+    torch.set_num_threads(1)
     env.reuse_buffers = True
 
     # extra (not the headline): two env batches in flight through step_async / step_wait, so that the upload +
@@ -820,6 +825,7 @@ def run_b200_arm(args, rank, local_rank, world):
                            "the two flip-flopped pinned result slabs (valid until the next-but-one step)",
                     "cpu_affinity": numa},
             "e2e_fresh_arrays": {"value": fresh_value, "unit": UNIT, "ms_per_step": 1e3 * fresh_max / k_e2e,
+                                 "host_copy_threads": host_threads,
                                  "api": "the same call with the default env.reuse_buffers = False: every step hands out "
                                         "freshly allocated host copies (the reference's ownership semantics)"},
             "value_two_batches_in_flight": {"value": total2 / max2, "unit": UNIT, "steps": K, "ms_per_step": 1e3 * max2 / K,
