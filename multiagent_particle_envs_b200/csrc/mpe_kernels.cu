@@ -46,11 +46,14 @@ struct Shape {
         return ((od / unit) | 1) * unit;
     }
     __host__ __device__ static constexpr bool obs_dense(int i) { return obs_pitch(i) == P::obs_dim(i); }
-    // a tile with a slot of its own is written by its agent's observe() and streamed out later together with the others;
-    // tiles without one share a slot (write, sync, stream, sync).  -DMPE_COMPACT_OBS=1 (A/B builds): every tile shares,
-    // which shrinks the staging of spread N=3 from 8.8 to 4.3 KB per warp (more blocks of the NEXT grid fit beside this one)
+    // Every observation tile of a warp shares ONE slot (write rows, sync, stream out, sync) -- MPE_COMPACT_OBS=1, the
+    // default since round 2.  With a private slot per dense tile (-DMPE_COMPACT_OBS=0, round 1: all rows written first,
+    // one sync, then streamed) the staging of world_comm was 22 KB per warp and shared memory capped residency at 10
+    // warps per SM; shared it is 6 KB (spread N=3: 8.8 -> 4.3 KB) and registers are the limit (16 warps per SM).
+    // Measured (profiles/r2f_sweep_{default,compact}.jsonl): world_comm 65 536 worlds 20.3 -> 15.7 us (0.58 -> 0.75 of
+    // the HBM peak), 32 768: 11.0 -> 10.0 us, 262 144: 58.6 -> 53.0 us; spread N=3 262 144: 18.7 -> 18.1 us; tag unchanged.
 #ifndef MPE_COMPACT_OBS
-#define MPE_COMPACT_OBS 0
+#define MPE_COMPACT_OBS 1
 #endif
     __host__ __device__ static constexpr bool obs_private(int i) { return obs_dense(i) && !MPE_COMPACT_OBS; }
     __host__ __device__ static constexpr int obs_floats(int i) { return (32 * obs_pitch(i) + 3) & ~3; }

@@ -289,3 +289,16 @@ def test_bench_shape_formula_equals_library(tag):
     R = bench.ring_size(ibpe, 65536)
     assert 0 < ibpe < bpe and (R == bench.MAX_RING or R * ibpe * 65536 > bench.L2_MULTIPLE * bench.L2_BYTES)
     assert bench.ring_size(ibpe, 1 << 26) == 3      # huge batches: the minimum ring
+
+
+def test_bench_numa_pinning_degrades_gracefully():
+    """without nvidia-smi / sysfs GPU entries (this container) the rank keeps its affinity and says so"""
+    sys.path.insert(0, ROOT)
+    import bench
+    before = os.sched_getaffinity(0)
+    orig, what = bench.pin_to_gpu_numa(0)
+    try:
+        assert orig == before and isinstance(what, str) and what
+        assert os.sched_getaffinity(0) <= before
+    finally:
+        os.sched_setaffinity(0, before)
