@@ -324,8 +324,16 @@ __device__ __forceinline__ void write_observations(const StepArgs &a, const DevD
 // the general kernel: with ~3 resident warps per scheduler the step is bound by each warp's own instruction stream,
 // and instruction-fetch stalls across the skipped cold blocks were ~8 % of it (profiles/).  Same arithmetic, same
 // order: bit-identical.  A ragged tail and every other flag combination run on the general kernel.
-template <class P, int MODE, bool SPLIT = false, bool HOT = false>
-__global__ void __launch_bounds__(MPE_BOUND_THREADS, MPE_MIN_BLOCKS) mpe_kernel(const __grid_constant__ StepArgs a) {
+//
+// DENSE (HOT only): the same code compiled for an 80-register budget (__launch_bounds__(128, 6): 24 instead of 16
+// resident warps per SM).  Only instantiated for programs that fit 80 registers without spilling (P::kLowRegVariant:
+// the tag family up to 6 agents, spread N=4) and only launched when the batch has more tiles than the 128-register
+// kernel keeps resident (> 148 x 16 warps): there occupancy wins (tag, 131 072 worlds: 13.1 -> 11.3 us, 0.75 -> 0.87
+// of the HBM peak; 262 144: 23.1 -> 22.0 us), below it the register-rich version is faster (65 536: 7.5 vs 7.8 us)
+// (profiles/r2g_sweep_{default,regs80}.jsonl).
+template <class P, int MODE, bool SPLIT = false, bool HOT = false, bool DENSE = false>
+__global__ void __launch_bounds__(DENSE ? 128 : MPE_BOUND_THREADS, DENSE ? 6 : MPE_MIN_BLOCKS) mpe_kernel(const __grid_constant__ StepArgs a) {
+    static_assert(!DENSE || HOT, "the low-register build exists for the HOT fused step only");
     static_assert(!SPLIT || MODE == kFusedStep, "warp pairs exist for the fused step only");
     static_assert(!HOT || (MODE == kFusedStep && !SPLIT && Shape<P>::all_act_dense()), "HOT = plain fused step, dense tiles");
     static_assert(!SPLIT || pair_count<P>() * 64 <= Shape<P>::kWarpFloats - Shape<P>::obs_base(), "pair exchange must fit the obs tiles");
@@ -985,6 +993,7 @@ struct Program {
     KernelFn fn[4];
     int smem_bytes;  // dynamic shared memory per WARP
     KernelFn hot_fn;    // fused step specialised for whole tiles / float actions / cp.async staging (null: no such program)
+    KernelFn hot_dense_fn;   // the same compiled for 80 registers (large batches of programs that fit without spilling)
     KernelFn split_fn;  // fused step with a warp PAIR per 32-world tile (small batches of heavy scenarios)
     KernelFn pipe_fn;   // software-pipelined persistent fused step (null unless every action tile is dense)
     int pipe_smem;      // dynamic shared memory per WARP of the pipelined kernel
@@ -1009,6 +1018,7 @@ static Program make_program() {
     if constexpr (P::A >= 2 && pair_count<P>() * 64 <= Shape<P>::kWarpFloats - Shape<P>::obs_base())
         p.split_fn = mpe_kernel<P, kFusedStep, true>;     // (the pair exchange must fit the observation tiles)
     if constexpr (Shape<P>::all_act_dense()) p.hot_fn = mpe_kernel<P, kFusedStep, false, true>;
+    if constexpr (Shape<P>::all_act_dense() && P::kLowRegVariant) p.hot_dense_fn = mpe_kernel<P, kFusedStep, false, true, true>;
     p.pipe_fn = Shape<P>::all_act_dense() ? mpe_pipe_kernel<P> : nullptr;
     p.pipe_smem = Shape<P>::kPipeWarpBytes;
     p.rollout_fn = mpe_rollout_kernel<P>;
@@ -1144,6 +1154,8 @@ extern "C" int mpe_create(const mpe_desc *desc, int64_t n_env, int device, mpe_h
         if (prog->hot_fn && prog->smem_bytes > 0)
             CUDA_TRY(cudaFuncSetAttribute(prog->hot_fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           prog->smem_bytes * max_warps_per_block(prog->smem_bytes)));
+        if (prog->hot_dense_fn && prog->smem_bytes > 0)
+            CUDA_TRY(cudaFuncSetAttribute(prog->hot_dense_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, prog->smem_bytes * 4));
         if (prog->pipe_fn)
             CUDA_TRY(cudaFuncSetAttribute(prog->pipe_fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           prog->pipe_smem * max_warps_per_block(prog->pipe_smem)));
@@ -1363,7 +1375,7 @@ static int launch(mpe_handle h, int mode, StepArgs &args, void *stream, int64_t 
     if (pdl_mode() == 5) args.flags |= kFlagPdlAfterIssue;
     if (cpasync) args.flags |= kFlagCpAsync;
     // one grid of autonomous warps over [sa.begin, sa.begin + sa.count)
-    auto launch_grid = [&](KernelFn fn, StepArgs &sa, bool pairs) -> int {
+    auto launch_grid = [&](KernelFn fn, StepArgs &sa, bool pairs, int max_wpb = kMaxWarpsPerBlock) -> int {
         int64_t nw = (sa.count + 31) / 32;
         if (pairs) nw *= 2;
         // Warps are autonomous, so the block size only sets scheduling granularity (measured at 65536 worlds:
@@ -1371,6 +1383,7 @@ static int launch(mpe_handle h, int mode, StepArgs &args, void *stream, int64_t 
         // that the few blocks spread over all 148 SMs, mid-size batches two, large ones four.
         int wpb = wpb_env ? wpb_env : (nw <= 148 * 4 ? 1 : (nw <= 148 * 64 ? 2 : 4));
         if (wpb > max_warps_per_block(h->prog->smem_bytes)) wpb = max_warps_per_block(h->prog->smem_bytes);
+        if (wpb > max_wpb) wpb = max_wpb;
         if (pairs) wpb = (wpb < 2) ? 2 : (wpb & ~1);      // a pair lives in one block
         const int64_t blocks = (nw + wpb - 1) / wpb;
         if (blocks > 0x7fffffffLL) return MPE_ERR_BAD_ARG;
@@ -1399,7 +1412,11 @@ static int launch(mpe_handle h, int mode, StepArgs &args, void *stream, int64_t 
     if (hot) {
         StepArgs ha = args;
         ha.count = args.count / 32 * 32;
-        rc = launch_grid(h->prog->hot_fn, ha, false);
+        // more tiles than the 128-register kernel keeps resident (16 warps per SM): the 80-register build, if there is one
+        static const int dense_env = [] { const char *e = getenv("MPE_B200_DENSE"); return e ? atoi(e) : -1; }();   // 0 never, 1 always
+        const bool dense = h->prog->hot_dense_fn != nullptr &&
+                           (dense_env == 1 || (dense_env < 0 && ha.count / 32 > 148LL * 16));
+        rc = dense ? launch_grid(h->prog->hot_dense_fn, ha, false, 4) : launch_grid(h->prog->hot_fn, ha, false);
         args.begin += ha.count;
         args.count -= ha.count;
     }

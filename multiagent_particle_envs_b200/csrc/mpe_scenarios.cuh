@@ -27,6 +27,8 @@ struct WorldRegs {
 struct ProgramBase {
     template <class W>
     __device__ __forceinline__ static void prepare(const DevDesc &, W &) {}
+    // true: also build the 80-register variant of the fused step (only for programs that fit without spilling)
+    static constexpr bool kLowRegVariant = false;
 };
 
 // v[idx] for a per-lane index without dynamic register indexing (select chain, N <= 8)
@@ -91,6 +93,7 @@ template <int N_>
 struct Spread : ProgramBase {
     static constexpr int A = N_, L = N_, DIMC = 2, NS = 0, INFO = 4, G = 0;
     static constexpr int kScenario = MPE_SCN_SPREAD;
+    static constexpr bool kLowRegVariant = (N_ == 4);
     using W = WorldRegs<A, L, 0>;
     __host__ __device__ static constexpr int obs_dim(int) { return 4 + 2 * L + 2 * (A - 1) + DIMC * (A - 1); }
     __host__ __device__ static constexpr int act_dim(int) { return 5; }
@@ -167,6 +170,7 @@ struct Tag : ProgramBase {
     static constexpr int NADV = NADV_, NGOOD = NGOOD_;
     static constexpr int A = NADV + NGOOD, L = L_, DIMC = 2, NS = 0, INFO = 1, G = 0;
     static constexpr int kScenario = MPE_SCN_TAG;
+    static constexpr bool kLowRegVariant = (A >= 3 && A <= 6);   // 3+1 and 4+2 fit 80 registers; 6+2 spills
     using W = WorldRegs<A, L, 0>;
     __host__ __device__ static constexpr bool adversary(int i) { return i < NADV; }
     __host__ __device__ static constexpr int obs_dim(int i) {                       // simple_tag.py:131-147

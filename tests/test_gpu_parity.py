@@ -377,6 +377,7 @@ np.savez(sys.argv[1], **out)
 
 ALT_KERNELS = {
     "general_kernel_instead_of_hot": {"MPE_B200_HOT": "0"},     # the un-specialised fused step for every tile
+    "low_register_build": {"MPE_B200_DENSE": "1"},                # the 80-register HOT variant (tag family, spread N=4)
     "warp_pair_split": {"MPE_B200_SPLIT": "1"},
     "software_pipelined_persistent": {"MPE_B200_PIPE": "1"},
 }
@@ -397,7 +398,7 @@ def test_alternative_step_kernels_are_bit_identical(tmp_path, variant):
     for mode in ("0", "1"):
         path = str(tmp_path / ("alt%s.npz" % mode))
         env = dict(os.environ)
-        for k in ("MPE_B200_SPLIT", "MPE_B200_PIPE", "MPE_B200_HOT"):
+        for k in ("MPE_B200_SPLIT", "MPE_B200_PIPE", "MPE_B200_HOT", "MPE_B200_DENSE"):
             env.pop(k, None)
         if mode == "1":
             env.update(ALT_KERNELS[variant])

@@ -57,10 +57,11 @@ def main():
     rows = []
     for mangled, (reg, stack) in usage.items():
         nm = names[mangled]
-        m = re.match(r"void mpe::mpe_kernel<mpe::(.+), 0, (false|true), (false|true)>\(", nm)
+        m = re.match(r"void mpe::mpe_kernel<mpe::(.+), 0, (false|true), (false|true), (false|true)>\(", nm)
         if not m:
             continue
-        label = m.group(1) + (" (warp pair)" if m.group(2) == "true" else "") + (" HOT" if m.group(3) == "true" else "")
+        label = (m.group(1) + (" (warp pair)" if m.group(2) == "true" else "") + (" HOT" if m.group(3) == "true" else "")
+                 + (" 80-reg" if m.group(4) == "true" else ""))
         c = mix.get(mangled, {})
         fp = sum(c[k] for k in ("FADD", "FMUL", "FFMA", "FSETP", "FSEL", "FMNMX", "FMNMX3"))
         rows.append((label, reg, stack, c["total"], fp, c["MUFU"], c["LDG"], c["LDGSTS"], c["LDS"], c["STS"], c["STG"],
