@@ -90,12 +90,9 @@ template <class P>
 __device__ __forceinline__ void physics(const DevDesc &d, typename P::W &w, const float (&ux)[P::A],
                                         const float (&uy)[P::A]) {
     constexpr int A = P::A, L = P::L;
-    float fx[A], fy[A];
+    float2 F[A];   // (x, y) force pairs: accumulated with packed FADD2 (bit-identical to two scalar adds)
 #pragma unroll
-    for (int i = 0; i < A; ++i) {  // apply_action_force (core.py:134-140)
-        fx[i] = ux[i];
-        fy[i] = uy[i];
-    }
+    for (int i = 0; i < A; ++i) F[i] = make_float2(ux[i], uy[i]);  // apply_action_force (core.py:134-140)
     const float k = d.contact_margin, cf = d.contact_force;
     // apply_environment_force (core.py:143-155): pairs (a, b), a < b, agents then landmarks.
     // Landmark-landmark pairs move nothing and are dropped at compile time.
@@ -112,23 +109,17 @@ __device__ __forceinline__ void physics(const DevDesc &d, typename P::W &w, cons
             const float bx = b_agent ? w.px[bi] : w.lx[bl];
             const float by = b_agent ? w.py[bi] : w.ly[bl];
             const float sb = b_agent ? d.a_size[bi] : d.l_size[bl];
-            const float2 f = pair_force(__fsub_rn(w.px[a], bx), __fsub_rn(w.py[a], by), __fadd_rn(d.a_size[a], sb),
-                                        cf, k, d.inv_margin);                // :186-193
-            if (P::movable(a)) {                                            // :194, 149-151
-                fx[a] = __fadd_rn(fx[a], f.x);
-                fy[a] = __fadd_rn(fy[a], f.y);
-            }
-            if (b_agent && P::movable(bi)) {                                // :195, 152-154
-                fx[bi] = __fsub_rn(fx[bi], f.x);
-                fy[bi] = __fsub_rn(fy[bi], f.y);
-            }
+            const float2 dl = sub2(make_float2(w.px[a], w.py[a]), make_float2(bx, by));
+            const float2 f = pair_force(dl.x, dl.y, __fadd_rn(d.a_size[a], sb), cf, k, d.inv_margin);   // :186-193
+            if (P::movable(a)) F[a] = __fadd2_rn(F[a], f);                  // :194, 149-151
+            if (b_agent && P::movable(bi)) F[bi] = sub2(F[bi], f);          // :195, 152-154
         }
     }
     // integrate_state (core.py:158-169)
 #pragma unroll
     for (int i = 0; i < A; ++i) {
         if (!P::movable(i)) continue;
-        const float4 r = integrate_entity<P::kSpeedLimit>(w.px[i], w.py[i], w.vx[i], w.vy[i], fx[i], fy[i], d.keep,
+        const float4 r = integrate_entity<P::kSpeedLimit>(w.px[i], w.py[i], w.vx[i], w.vy[i], F[i].x, F[i].y, d.keep,
                                                           d.a_dt_over_mass[i], d.dt, d.a_max_speed[i]);
         w.px[i] = r.x; w.py[i] = r.y; w.vx[i] = r.z; w.vy[i] = r.w;
     }
@@ -176,8 +167,8 @@ __device__ __forceinline__ void physics_split(const DevDesc &d, typename P::W &w
                     const float bx = b_agent ? w.px[bi] : w.lx[bl];
                     const float by = b_agent ? w.py[bi] : w.ly[bl];
                     const float sb = b_agent ? d.a_size[bi] : d.l_size[bl];
-                    ex[idx * 32 + lane] = pair_force(__fsub_rn(w.px[a], bx), __fsub_rn(w.py[a], by),
-                                                     __fadd_rn(d.a_size[a], sb), cf, k, d.inv_margin);
+                    const float2 dl = sub2(make_float2(w.px[a], w.py[a]), make_float2(bx, by));
+                    ex[idx * 32 + lane] = pair_force(dl.x, dl.y, __fadd_rn(d.a_size[a], sb), cf, k, d.inv_margin);
                 }
             }
         });

@@ -73,7 +73,7 @@ struct Simple : ProgramBase {
     __device__ __forceinline__ static void observe(const DevDesc &, const W &w, Wr &o) {
         o.put2(w.vx[I], w.vy[I]);                                                    // :50
 #pragma unroll
-        for (int l = 0; l < L; ++l) o.put2(w.lx[l] - w.px[I], w.ly[l] - w.py[I]);    // :48-49
+        for (int l = 0; l < L; ++l) o.put2(sub2(make_float2(w.lx[l], w.ly[l]), make_float2(w.px[I], w.py[I])));    // :48-49
     }
     __device__ __forceinline__ static void reward(const DevDesc &, const W &w, float (&rew)[A], float *) {
 #pragma unroll
@@ -108,10 +108,10 @@ struct Spread : ProgramBase {
         o.put2(w.vx[I], w.vy[I]);                                                    // simple_spread.py:100
         o.put2(w.px[I], w.py[I]);
 #pragma unroll
-        for (int l = 0; l < L; ++l) o.put2(w.lx[l] - w.px[I], w.ly[l] - w.py[I]);    // :87-88
+        for (int l = 0; l < L; ++l) o.put2(sub2(make_float2(w.lx[l], w.ly[l]), make_float2(w.px[I], w.py[I])));    // :87-88
 #pragma unroll
         for (int j = 0; j < A; ++j)
-            if (j != I) o.put2(w.px[j] - w.px[I], w.py[j] - w.py[I]);                // :99
+            if (j != I) o.put2(sub2(make_float2(w.px[j], w.py[j]), make_float2(w.px[I], w.py[I])));                // :99
 #pragma unroll
         for (int j = 0; j < (A - 1) * DIMC; ++j) o.put(0.0f);                        // :98 (all agents silent)
     }
@@ -188,10 +188,10 @@ struct Tag : ProgramBase {
         o.put2(w.vx[I], w.vy[I]);                                                    // :147
         o.put2(w.px[I], w.py[I]);
 #pragma unroll
-        for (int l = 0; l < L; ++l) o.put2(w.lx[l] - w.px[I], w.ly[l] - w.py[I]);    // :133-136
+        for (int l = 0; l < L; ++l) o.put2(sub2(make_float2(w.lx[l], w.ly[l]), make_float2(w.px[I], w.py[I])));    // :133-136
 #pragma unroll
         for (int j = 0; j < A; ++j)
-            if (j != I) o.put2(w.px[j] - w.px[I], w.py[j] - w.py[I]);                // :144
+            if (j != I) o.put2(sub2(make_float2(w.px[j], w.py[j]), make_float2(w.px[I], w.py[I])));                // :144
 #pragma unroll
         for (int j = NADV; j < A; ++j)
             if (j != I) o.put2(w.vx[j], w.vy[j]);                                    // :145-146
@@ -279,7 +279,7 @@ struct WorldComm : ProgramBase {
         o.put2(w.vx[I], w.vy[I]);
         o.put2(w.px[I], w.py[I]);
 #pragma unroll
-        for (int l = 0; l < L; ++l) o.put2(w.lx[l] - w.px[I], w.ly[l] - w.py[I]);    // :226-229
+        for (int l = 0; l < L; ++l) o.put2(sub2(make_float2(w.lx[l], w.ly[l]), make_float2(w.px[I], w.py[I])));    // :226-229
         const bool f0 = in_forest(d, w, I, 0), f1 = in_forest(d, w, I, 1);
         bool vis[A];
 #pragma unroll
@@ -289,7 +289,10 @@ struct WorldComm : ProgramBase {
         }
 #pragma unroll
         for (int j = 0; j < A; ++j)
-            if (j != I) o.put2(vis[j] ? w.px[j] - w.px[I] : 0.0f, vis[j] ? w.py[j] - w.py[I] : 0.0f);
+            if (j != I) {
+                const float2 r = sub2(make_float2(w.px[j], w.py[j]), make_float2(w.px[I], w.py[I]));
+                o.put2(vis[j] ? r.x : 0.0f, vis[j] ? r.y : 0.0f);
+            }
         if (adversary(I)) {
 #pragma unroll
             for (int j = NADV; j < A; ++j)
@@ -384,12 +387,12 @@ struct Adversary : ProgramBase {
 
     template <int I, class Wr>
     __device__ __forceinline__ static void observe(const DevDesc &, const W &w, Wr &o) {
-        if (!adversary(I)) o.put2(pick(w.lx, w.g[0]) - w.px[I], pick(w.ly, w.g[0]) - w.py[I]);   // :136
+        if (!adversary(I)) o.put2(sub2(make_float2(pick(w.lx, w.g[0]), pick(w.ly, w.g[0])), make_float2(w.px[I], w.py[I])));   // :136
 #pragma unroll
-        for (int l = 0; l < L; ++l) o.put2(w.lx[l] - w.px[I], w.ly[l] - w.py[I]);                  // :123-125
+        for (int l = 0; l < L; ++l) o.put2(sub2(make_float2(w.lx[l], w.ly[l]), make_float2(w.px[I], w.py[I])));                  // :123-125
 #pragma unroll
         for (int j = 0; j < A; ++j)
-            if (j != I) o.put2(w.px[j] - w.px[I], w.py[j] - w.py[I]);                              // :131-133
+            if (j != I) o.put2(sub2(make_float2(w.px[j], w.py[j]), make_float2(w.px[I], w.py[I])));                              // :131-133
     }
     __device__ __forceinline__ static void reward(const DevDesc &, const W &w, float (&rew)[A], float *info) {
         const float gx = pick(w.lx, w.g[0]), gy = pick(w.ly, w.g[0]);
@@ -451,12 +454,12 @@ struct Push : ProgramBase {
     __device__ __forceinline__ static void observe(const DevDesc &, const W &w, Wr &o) {
         o.put2(w.vx[I], w.vy[I]);
         if (!adversary(I)) {
-            o.put2(pick(w.lx, w.g[0]) - w.px[I], pick(w.ly, w.g[0]) - w.py[I]);       // :93
+            o.put2(sub2(make_float2(pick(w.lx, w.g[0]), pick(w.ly, w.g[0])), make_float2(w.px[I], w.py[I])));       // :93
 #pragma unroll
             for (int c = 0; c < 3; ++c) o.put(w.g[0] + 1 == c ? 0.25f + 0.5f : 0.25f); // agent.color (:47-53)
         }
 #pragma unroll
-        for (int l = 0; l < L; ++l) o.put2(w.lx[l] - w.px[I], w.ly[l] - w.py[I]);
+        for (int l = 0; l < L; ++l) o.put2(sub2(make_float2(w.lx[l], w.ly[l]), make_float2(w.px[I], w.py[I])));
         if (!adversary(I)) {
 #pragma unroll
             for (int l = 0; l < L; ++l)
@@ -465,7 +468,7 @@ struct Push : ProgramBase {
         }
 #pragma unroll
         for (int j = 0; j < A; ++j)
-            if (j != I) o.put2(w.px[j] - w.px[I], w.py[j] - w.py[I]);
+            if (j != I) o.put2(sub2(make_float2(w.px[j], w.py[j]), make_float2(w.px[I], w.py[I])));
     }
     __device__ __forceinline__ static void reward(const DevDesc &, const W &w, float (&rew)[A], float *) {
         const float gx = pick(w.lx, w.g[0]), gy = pick(w.ly, w.g[0]);
@@ -507,7 +510,7 @@ struct SpeakerListener : ProgramBase {
         } else {                                                                     // :90-92
             o.put2(w.vx[1], w.vy[1]);
 #pragma unroll
-            for (int l = 0; l < L; ++l) o.put2(w.lx[l] - w.px[1], w.ly[l] - w.py[1]);
+            for (int l = 0; l < L; ++l) o.put2(sub2(make_float2(w.lx[l], w.ly[l]), make_float2(w.px[1], w.py[1])));
 #pragma unroll
             for (int q = 0; q < DIMC; ++q) o.put(w.c[q]);
         }
@@ -540,7 +543,7 @@ struct Reference : ProgramBase {
     __device__ __forceinline__ static void observe(const DevDesc &, const W &w, Wr &o) {
         o.put2(w.vx[I], w.vy[I]);                                                    // :80
 #pragma unroll
-        for (int l = 0; l < L; ++l) o.put2(w.lx[l] - w.px[I], w.ly[l] - w.py[I]);
+        for (int l = 0; l < L; ++l) o.put2(sub2(make_float2(w.lx[l], w.ly[l]), make_float2(w.px[I], w.py[I])));
 #pragma unroll
         for (int c = 0; c < 3; ++c) o.put(w.g[I] == c ? 0.75f : 0.25f);              // goal_b colour :64-66
 #pragma unroll
