@@ -1369,10 +1369,11 @@ static int launch(mpe_handle h, int mode, StepArgs &args, void *stream, int64_t 
     auto launch_grid = [&](KernelFn fn, StepArgs &sa, bool pairs, int max_wpb = kMaxWarpsPerBlock) -> int {
         int64_t nw = (sa.count + 31) / 32;
         if (pairs) nw *= 2;
-        // Warps are autonomous, so the block size only sets scheduling granularity (measured at 65536 worlds:
-        // 1 / 2 / 4 warps per block = 6.69 / 6.34 / 7.06 us per step): tiny batches use one warp per block so
-        // that the few blocks spread over all 148 SMs, mid-size batches two, large ones four.
-        int wpb = wpb_env ? wpb_env : (nw <= 148 * 4 ? 1 : (nw <= 148 * 64 ? 2 : 4));
+        // Warps are autonomous, so the block size only sets scheduling granularity.  While every warp of the batch is
+        // resident at once (<= 16 per SM) one warp per block balances the SMs best (world_comm, 32 768 worlds = 6.9
+        // warps per SM: 9.03 vs 9.60 us with two; spread N=3 and tag at 65 536 worlds: 1 and 2 tie, 4 loses 10 %,
+        // profiles/r2f_geometry_*, r2j_*); mid-size batches use two, large ones four.
+        int wpb = wpb_env ? wpb_env : (nw <= 148 * 16 ? 1 : (nw <= 148 * 64 ? 2 : 4));
         if (wpb > max_warps_per_block(h->prog->smem_bytes)) wpb = max_warps_per_block(h->prog->smem_bytes);
         if (wpb > max_wpb) wpb = max_wpb;
         if (pairs) wpb = (wpb < 2) ? 2 : (wpb & ~1);      // a pair lives in one block
