@@ -35,7 +35,6 @@ cpu_baseline  the reference path on the host cores beside the GPU number (N=1): 
 """
 import argparse
 import json
-import math
 import os
 import subprocess
 import sys
