@@ -191,6 +191,21 @@ MPE_API int mpe_rollout(mpe_handle h, void *agent_pv_dev, const void *lm_p_dev, 
                         float *const *obs_n_dev, float *rew_sum_dev, float *rew_steps_dev, uint8_t *done_dev,
                         uint32_t flags, void *stream);
 
+/* n_steps consecutive MultiAgentEnv.step calls in ONE launch with the policy INSIDE the kernel (the trainer's loop
+ * obs -> actor network -> env.step, bin/interactive.py:27-39 with `policy.action(obs_n[i])` being a small actor): agent i
+ * acts with  a_i = softmax(W2_i . relu(W1_i^T . obs_i + b1_i) + b2_i),  obs_dim_i -> hidden -> 5 movement probabilities.
+ * w1_n[i]: float [obs_dim_i][hidden] (input-major, 16-byte aligned), b1_n[i]: [hidden], w2_n[i]: [5][hidden], b2_n[i]: [5];
+ * hidden = 32 or 64.  World state stays in registers, observations are never written between steps.  Outputs as
+ * mpe_rollout; act_record_n (NULL or per agent float [n_steps][n_env][5]) receives the actions taken -- feeding them to
+ * mpe_rollout / mpe_step reproduces state, observations and reward sums bit for bit.  Only for scenarios whose agents
+ * all move and are silent and for which the program was built (the BASELINE.json worlds simple, simple_spread N = 3,
+ * simple_tag 3 + 1); otherwise MPE_ERR_UNSUPPORTED. */
+MPE_API int mpe_rollout_policy(mpe_handle h, void *agent_pv_dev, const void *lm_p_dev, float *comm_dev,
+                               const int32_t *goal_dev, const float *const *w1_n, const float *const *b1_n,
+                               const float *const *w2_n, const float *const *b2_n, int32_t hidden, int32_t n_steps,
+                               float *const *obs_n_dev, float *rew_sum_dev, float *rew_steps_dev,
+                               float *const *act_record_n, uint8_t *done_dev, uint32_t flags, void *stream);
+
 /* Same step for a caller that holds HOST buffers (what the reference's callers hold):
  * act_n_host[i] -> (async H2D into act_n_dev[i]) -> mpe_step -> (async D2H) obs_n_host[i],
  * rew_host, done_host, all ordered on `stream`.  Host buffers should be pinned for the copies

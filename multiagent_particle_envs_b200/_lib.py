@@ -84,6 +84,8 @@ _SIGNATURES = {
     "mpe_observe": (ctypes.c_int, [_P, _P, _P, _P, _P, _PP, _P, _P, _P, ctypes.c_uint32, _P]),
     "mpe_step": (ctypes.c_int, [_P, _P, _P, _P, _P, _PP, _PP, _P, _P, _P, ctypes.c_uint32, _P]),
     "mpe_rollout": (ctypes.c_int, [_P, _P, _P, _P, _P, _PP, ctypes.c_int32, _PP, _P, _P, _P, ctypes.c_uint32, _P]),
+    "mpe_rollout_policy": (ctypes.c_int, [_P, _P, _P, _P, _P, _PP, _PP, _PP, _PP, ctypes.c_int32, ctypes.c_int32, _PP, _P, _P,
+                                          _PP, _P, ctypes.c_uint32, _P]),
     "mpe_step_host": (ctypes.c_int, [_P, _P, _P, _P, _P, _PP, _PP, _PP, _P, _P, _P, _PP, _P, _P, _P,
                                      ctypes.c_uint32, _P]),
     "mpe_strerror": (ctypes.c_char_p, [ctypes.c_int]),

@@ -786,6 +786,216 @@ __global__ void __launch_bounds__(MPE_BOUND_THREADS, MPE_MIN_BLOCKS) mpe_rollout
     }
 }
 
+
+// ---- K-step CLOSED-LOOP rollout with an in-kernel policy (the persistent form with a device-
+// resident policy) -------------------------------------------------------------------------------
+// T consecutive MultiAgentEnv.step calls in ONE launch where every agent's action is produced inside the kernel by its
+// own two-layer perceptron  a_i = softmax(W2_i . relu(W1_i^T . obs_i + b1_i) + b2_i)  (obs_dim_i -> H -> 5 movement
+// probabilities, the MADDPG actor shape).  A world's state lives in registers for all T steps; an agent's observation
+// is produced straight into registers (never written), pushed through the perceptron (weights of all agents sit in
+// shared memory once per block, read as broadcast LDS.128), decoded and integrated.  Per step NOTHING is read from HBM
+// and only the optional records (rewards, actions) are written; observations are written for the final state.
+// Scenarios whose agents all move and are silent (simple_spread, simple_tag, ...).  The physics / reward / observation
+// arithmetic is the fused step's: feeding the recorded actions to T fused steps reproduces the final state, the
+// observations and the reward sums bit for bit; the perceptron matches a float64 evaluation to ~1e-6 (tests).
+struct PolicyArgs {
+    StepArgs s;
+    int32_t T;
+    float *rew_steps;               // [T][A][n] or null
+    float *act_rec[kMaxA];          // [T][n][5] per agent, or null
+    const float *w1[kMaxA];         // [obs_dim_i][H]  (input-major: W1^T of a torch Linear(obs_dim_i, H))
+    const float *b1[kMaxA];         // [H]
+    const float *w2[kMaxA];         // [5][H]          (the layout of a torch Linear(H, 5).weight)
+    const float *b2[kMaxA];         // [5]
+};
+
+template <class P, int H>
+struct PolicyShape {
+    __host__ __device__ static constexpr int agent_floats(int i) { return P::obs_dim(i) * H + H + 5 * H + 8; }
+    __host__ __device__ static constexpr int agent_off(int i) { int s = 0; for (int j = 0; j < i; ++j) s += agent_floats(j); return s; }
+    static constexpr int kWeightFloats = (agent_off(P::A) + 3) & ~3;
+};
+
+// observation writer into registers (every index is a compile-time constant after unrolling)
+template <int DIM>
+struct RegWriter {
+    float v[DIM];
+    int k = 0;
+    __device__ __forceinline__ void put(float x) { v[k++] = x; }
+    __device__ __forceinline__ void put2(float a, float b) { v[k] = a; v[k + 1] = b; k += 2; }
+    __device__ __forceinline__ void put2(float2 a) { put2(a.x, a.y); }
+};
+
+
+// one agent of the in-kernel policy: observation -> registers -> two-layer perceptron -> softmax -> decoded (u.x, u.y).
+// A plain force-inlined function with unrolled loops (not a lambda: arrays captured by reference by a lambda that the
+// compiler declines to inline end up in local memory).  W = [W1: OD x H][b1: H][W2: 5 x H][b2: 5] in shared memory.
+template <class P, int H, int I>
+__device__ __forceinline__ float2 policy_agent(const DevDesc &d, const typename P::W &w, const float *__restrict__ W,
+                                               float *__restrict__ record) {
+    constexpr int OD = P::obs_dim(I);
+    const float *W1 = W, *B1 = W1 + OD * H, *W2 = B1 + H, *B2 = W2 + 5 * H;
+    RegWriter<OD> o;
+    P::template observe<I>(d, w, o);                       // scenario.observation(agent I) -> registers
+    float h[H];
+#pragma unroll
+    for (int q = 0; q < H; q += 4) {
+        const float4 b = *reinterpret_cast<const float4 *>(B1 + q);
+        h[q] = b.x; h[q + 1] = b.y; h[q + 2] = b.z; h[q + 3] = b.w;
+    }
+#pragma unroll
+    for (int j = 0; j < OD; ++j) {                         // h += obs[j] * W1[j][:]   (ascending j, FMA)
+        const float oj = o.v[j];
+#pragma unroll
+        for (int q = 0; q < H; q += 4) {
+            const float4 wv = *reinterpret_cast<const float4 *>(W1 + j * H + q);
+            h[q] = __fmaf_rn(oj, wv.x, h[q]);
+            h[q + 1] = __fmaf_rn(oj, wv.y, h[q + 1]);
+            h[q + 2] = __fmaf_rn(oj, wv.z, h[q + 2]);
+            h[q + 3] = __fmaf_rn(oj, wv.w, h[q + 3]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < H; ++q) h[q] = fmaxf(h[q], 0.0f);  // ReLU
+    float lg[5];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {                          // logits[c] = b2[c] + sum_q h[q] * W2[c][q]  (ascending q)
+        float acc = B2[c];
+#pragma unroll
+        for (int q = 0; q < H; q += 4) {
+            const float4 wv = *reinterpret_cast<const float4 *>(W2 + c * H + q);
+            acc = __fmaf_rn(h[q], wv.x, acc);
+            acc = __fmaf_rn(h[q + 1], wv.y, acc);
+            acc = __fmaf_rn(h[q + 2], wv.z, acc);
+            acc = __fmaf_rn(h[q + 3], wv.w, acc);
+        }
+        lg[c] = acc;
+    }
+    const float m = fmaxf(fmaxf(fmaxf(lg[0], lg[1]), fmaxf(lg[2], lg[3])), lg[4]);
+    float e[5], sum = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) { e[c] = expf(__fsub_rn(lg[c], m)); sum = __fadd_rn(sum, e[c]); }
+    float pr[5];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) pr[c] = __fdiv_rn(e[c], sum);                // softmax: the action vector
+    if (record != nullptr) {
+#pragma unroll
+        for (int c = 0; c < 5; ++c) record[c] = pr[c];
+    }
+    // _set_action (environment.py:173-181), the arithmetic of decode_rows
+    float x = 0.0f, y = 0.0f;
+    x += pr[1] - pr[2];
+    y += pr[3] - pr[4];
+    return make_float2(__fmul_rn(x, d.a_sens[I]), __fmul_rn(y, d.a_sens[I]));
+}
+
+template <class P, int H>
+__global__ void __launch_bounds__(128) mpe_policy_rollout_kernel(const __grid_constant__ PolicyArgs pa) {
+    static_assert(P::NS == 0 && H % 4 == 0, "policy rollout: silent agents, hidden width a multiple of 4");
+    constexpr int A = P::A, L = P::L;
+    using PS = PolicyShape<P, H>;
+    const StepArgs &a = pa.s;
+    extern __shared__ __align__(16) float smem[];
+    float *s_w = smem;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // ---- all agents' weights -> shared memory, once per block ------------------------------------------------
+    static_for<A>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        constexpr int OD = P::obs_dim(i);
+        float *base = s_w + PS::agent_off(i);
+        for (int q = threadIdx.x; q < OD * H; q += blockDim.x) base[q] = pa.w1[i][q];
+        for (int q = threadIdx.x; q < H; q += blockDim.x) base[OD * H + q] = pa.b1[i][q];
+        for (int q = threadIdx.x; q < 5 * H; q += blockDim.x) base[OD * H + H + q] = pa.w2[i][q];
+        for (int q = threadIdx.x; q < 5; q += blockDim.x) base[OD * H + H + 5 * H + q] = pa.b2[i][q];
+    });
+    __syncthreads();
+
+    const int64_t n = a.n;
+    const int64_t end = a.begin + a.count;
+    const int64_t w0 = a.begin + (static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + warp) * 32;
+    if (w0 >= end) return;
+    const int rows = (end - w0) < 32 ? static_cast<int>(end - w0) : 32;
+    const bool active = lane < rows;
+    const int64_t wi = w0 + (active ? lane : 0);
+    float *s_warp = smem + PS::kWeightFloats + warp * Shape<P>::kWarpFloats;
+    const DevDesc &d = a.d;
+
+    typename P::W w;
+#pragma unroll
+    for (int i = 0; i < A; ++i) {
+        const float4 v = state_load(a.pv + i * n + wi);
+        w.px[i] = v.x; w.py[i] = v.y; w.vx[i] = v.z; w.vy[i] = v.w;
+    }
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+        const float2 v = state_load(a.lm + l * n + wi);
+        w.lx[l] = v.x; w.ly[l] = v.y;
+    }
+    if constexpr (P::G > 0) {
+#pragma unroll
+        for (int q = 0; q < P::G; ++q) w.g[q] = a.goal[q * n + wi];
+    }
+
+    float rsum[A];
+#pragma unroll
+    for (int i = 0; i < A; ++i) rsum[i] = 0.0f;
+#pragma unroll 1
+    for (int t = 0; t < pa.T; ++t) {
+        float ux[A], uy[A];
+        P::prepare(d, w);
+        static_for<A>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            const float2 u = policy_agent<P, H, i>(d, w, s_w + PolicyShape<P, H>::agent_off(i),
+                                                   (pa.act_rec[i] != nullptr && active)
+                                                       ? pa.act_rec[i] + (static_cast<int64_t>(t) * n + wi) * 5 : nullptr);
+            ux[i] = u.x;
+            uy[i] = u.y;
+        });
+        physics<P>(d, w, ux, uy);
+        float rew[A];
+        P::reward(d, w, rew, nullptr);
+        if (a.flags & MPE_FLAG_SHARED_REWARD) {
+            float sum = 0.0f;
+#pragma unroll
+            for (int i = 0; i < A; ++i) sum += rew[i];
+#pragma unroll
+            for (int i = 0; i < A; ++i) rew[i] = sum;
+        }
+#pragma unroll
+        for (int i = 0; i < A; ++i) rsum[i] = __fadd_rn(rsum[i], rew[i]);
+        if (pa.rew_steps != nullptr && active) {
+#pragma unroll
+            for (int i = 0; i < A; ++i) pa.rew_steps[(static_cast<int64_t>(t) * A + i) * n + wi] = rew[i];
+        }
+    }
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < A; ++i)
+            if (P::movable(i)) a.pv[i * n + wi] = make_float4(w.px[i], w.py[i], w.vx[i], w.vy[i]);
+    }
+    P::prepare(d, w);
+    write_observations<P>(a, d, w, s_warp, lane, rows, active, w0, wi, -1);
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < A; ++i) {
+            a.rew[i * n + wi] = rsum[i];
+            a.done[i * n + wi] = 0;
+        }
+    }
+}
+
+template <class P>
+constexpr bool policy_rollout_ok() {     // every agent moves, nobody speaks: the action is the 5-vector of probabilities
+    bool ok = P::NS == 0;
+    for (int i = 0; i < P::A; ++i) ok = ok && P::movable(i) && P::act_dim(i) == 5;
+    return ok;
+}
+// built for the BASELINE.json worlds (each instantiation unrolls obs_dim x H FMAs per agent: compile time)
+template <class P> struct PolicyBuilt { static constexpr bool value = false; };
+template <> struct PolicyBuilt<Simple<1, 1>> { static constexpr bool value = true; };
+template <> struct PolicyBuilt<Spread<3>> { static constexpr bool value = true; };
+template <> struct PolicyBuilt<Tag<3, 1, 2>> { static constexpr bool value = true; };
+
 // ---- generic program for user scenarios (MPE_SCN_CUSTOM) ------------------------------------------
 // Any entity table, flags read at run time; same arithmetic primitives and the same (a, b) pair order as
 // the compiled programs, so for a table that matches a built-in scenario the state is bit-identical.
@@ -988,6 +1198,8 @@ struct Program {
     KernelFn split_fn;  // fused step with a warp PAIR per 32-world tile (small batches of heavy scenarios)
     KernelFn pipe_fn;   // software-pipelined persistent fused step (null unless every action tile is dense)
     int pipe_smem;      // dynamic shared memory per WARP of the pipelined kernel
+    void (*policy_fn[2])(PolicyArgs);  // K-step closed-loop rollout, hidden width 32 / 64 (null: not built for this program)
+    int policy_weight_floats[2];
     void (*rollout_fn)(RolloutArgs);   // K-step open-loop rollout
     int rollout_smem;   // dynamic shared memory per WARP of the rollout kernel
     KernelFn lanes_fn;  // lane-per-agent fused step (simple_spread only), else null
@@ -1014,6 +1226,13 @@ static Program make_program() {
     p.pipe_smem = Shape<P>::kPipeWarpBytes;
     p.rollout_fn = mpe_rollout_kernel<P>;
     p.rollout_smem = Shape<P>::kRolloutWarpBytes;
+    // the closed-loop rollout is built for the BASELINE.json scenarios whose agents all move and are silent
+    if constexpr (policy_rollout_ok<P>() && PolicyBuilt<P>::value) {
+        p.policy_fn[0] = mpe_policy_rollout_kernel<P, 32>;
+        p.policy_fn[1] = mpe_policy_rollout_kernel<P, 64>;
+        p.policy_weight_floats[0] = PolicyShape<P, 32>::kWeightFloats;
+        p.policy_weight_floats[1] = PolicyShape<P, 64>::kWeightFloats;
+    }
     p.smem_bytes = Shape<P>::kWarpBytes;  // per warp
     p.A = P::A; p.L = P::L; p.NS = P::NS; p.DIMC = P::DIMC; p.INFO = P::INFO; p.G = P::G;
     for (int i = 0; i < P::A; ++i) { p.obs_dim[i] = P::obs_dim(i); p.act_dim[i] = P::act_dim(i); }
@@ -1150,6 +1369,10 @@ extern "C" int mpe_create(const mpe_desc *desc, int64_t n_env, int device, mpe_h
         if (prog->pipe_fn)
             CUDA_TRY(cudaFuncSetAttribute(prog->pipe_fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           prog->pipe_smem * max_warps_per_block(prog->pipe_smem)));
+        for (int k = 0; k < 2; ++k)
+            if (prog->policy_fn[k])
+                CUDA_TRY(cudaFuncSetAttribute(prog->policy_fn[k], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              prog->policy_weight_floats[k] * 4 + prog->smem_bytes * 4));
         if (prog->rollout_fn)
             CUDA_TRY(cudaFuncSetAttribute(prog->rollout_fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           prog->rollout_smem * max_warps_per_block(prog->rollout_smem)));
@@ -1548,6 +1771,55 @@ extern "C" int mpe_rollout(mpe_handle h, void *pv, const void *lm, float *comm, 
                                      static_cast<cudaStream_t>(stream));
     if (prev != h->device) cudaSetDevice(prev);
     if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernel(rollout)");
+    __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED);
+    return MPE_OK;
+}
+
+extern "C" int mpe_rollout_policy(mpe_handle h, void *pv, const void *lm, float *comm, const int32_t *goal,
+                                  const float *const *w1_n, const float *const *b1_n, const float *const *w2_n,
+                                  const float *const *b2_n, int32_t hidden, int32_t n_steps, float *const *obs_n,
+                                  float *rew_sum, float *rew_steps, float *const *act_record_n, uint8_t *done,
+                                  uint32_t flags, void *stream) {
+    if (!h || n_steps < 0 || !w1_n || !b1_n || !w2_n || !b2_n) return MPE_ERR_BAD_ARG;
+    if (h->device < 0) return MPE_ERR_NO_DEVICE;
+    const int k = hidden == 32 ? 0 : (hidden == 64 ? 1 : -1);
+    if (k < 0 || h->prog->scenario == MPE_SCN_CUSTOM || h->prog->policy_fn[k] == nullptr) return MPE_ERR_UNSUPPORTED;
+    if (flags & (MPE_FLAG_DISCRETE_ACTION_INPUT | MPE_FLAG_FORCE_DISCRETE_ACTION)) return MPE_ERR_UNSUPPORTED;
+    if (rew_steps != nullptr && !ok4(rew_steps)) return MPE_ERR_BAD_ARG;
+    NvtxRange range("mpe_rollout_policy");
+    PolicyArgs pa{};
+    StepArgs &a = pa.s;
+    int r = fill_state(h, a, pv, lm, comm, goal);
+    if (r) return r;
+    r = fill_outputs(h, a, obs_n, rew_sum, done, nullptr);
+    if (r) return r;
+    for (int i = 0; i < h->prog->A; ++i) {
+        if (!ok16(w1_n[i]) || !ok16(b1_n[i]) || !ok16(w2_n[i]) || !ok4(b2_n[i])) return MPE_ERR_BAD_ARG;
+        pa.w1[i] = w1_n[i]; pa.b1[i] = b1_n[i]; pa.w2[i] = w2_n[i]; pa.b2[i] = b2_n[i];
+        pa.act_rec[i] = act_record_n ? act_record_n[i] : nullptr;
+        if (pa.act_rec[i] != nullptr && !ok4(pa.act_rec[i])) return MPE_ERR_BAD_ARG;
+    }
+    a.info = nullptr;
+    a.flags = flags;
+    a.d = h->dev;
+    a.n = h->n;
+    a.begin = 0;
+    a.count = h->n;
+    pa.T = n_steps;
+    pa.rew_steps = rew_steps;
+    const int64_t warps = (h->n + 31) / 32;
+    const int wpb = warps <= 148 * 16 ? 1 : (warps <= 148 * 64 ? 2 : 4);
+    const int64_t blocks = (warps + wpb - 1) / wpb;
+    if (blocks > 0x7fffffffLL) return MPE_ERR_BAD_ARG;
+    int prev = 0;
+    CUDA_TRY(cudaGetDevice(&prev));
+    if (prev != h->device) CUDA_TRY(cudaSetDevice(h->device));
+    void *params[] = {&pa};
+    const size_t smem = static_cast<size_t>(h->prog->policy_weight_floats[k]) * 4 + static_cast<size_t>(h->prog->smem_bytes) * wpb;
+    cudaError_t e = cudaLaunchKernel(reinterpret_cast<const void *>(h->prog->policy_fn[k]), dim3(static_cast<unsigned>(blocks)),
+                                     dim3(32 * wpb), params, smem, static_cast<cudaStream_t>(stream));
+    if (prev != h->device) cudaSetDevice(prev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernel(rollout_policy)");
     __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED);
     return MPE_OK;
 }

@@ -240,6 +240,55 @@ class MultiAgentEnv(_Env):
             return obs_n, reward_n, done_n, info_n, rew_steps
         return obs_n, reward_n, done_n, info_n
 
+    def rollout_policy(self, policies, n_steps, record_actions=False, per_step_rewards=False):
+        """T closed-loop steps in ONE kernel launch with the actors inside the kernel (mpe_rollout_policy): agent i acts
+        with softmax(W2_i relu(W1_i obs_i + b1_i) + b2_i).  policies[i] is a `torch.nn.Sequential(Linear(obs_dim_i, H),
+        ReLU(), Linear(H, 5))` or the tuple (W1 [H, obs_dim_i], b1 [H], W2 [5, H], b2 [5]) in torch's Linear layout, H = 32
+        or 64.  Returns (obs_n, reward_sum_n, done_n, info_n, extras) for the state after the last step; extras["actions"]
+        (record_actions) is a list of [T, N, 5] tensors with the actions taken, extras["rewards"] (per_step_rewards) a
+        [T, n, N] tensor.  World state lives in registers for all T steps and no observation is written in between.
+        Batched CUDA mode; scenarios whose agents all move and are silent and whose program was built with the policy
+        kernel (simple, simple_spread N=3, simple_tag 3+1) -- anything else raises."""
+        import torch
+        world = self.world
+        if not world.batched:
+            raise ValueError("rollout_policy needs a batched env (make_env(..., num_envs=N))")
+        if self._custom or self.discrete_action_input or self.force_discrete_action:
+            raise NotImplementedError("rollout_policy: compiled scenarios with plain action vectors only")
+        if len(policies) != self.n:
+            raise ValueError("expected %d policies, got %d" % (self.n, len(policies)))
+        nw = world.bind()
+        N, T = nw.n_env, int(n_steps)
+        keep, hidden = [], None
+        ptrs = ([], [], [], [])
+        for i, pol in enumerate(policies):
+            if isinstance(pol, torch.nn.Module):
+                lin = [m for m in pol.modules() if isinstance(m, torch.nn.Linear)]
+                if len(lin) != 2:
+                    raise ValueError("policy %d must be Linear -> ReLU -> Linear" % i)
+                pol = (lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias)
+            W1, b1, W2, b2 = [t.detach().to(device=nw.device, dtype=torch.float32) for t in pol]
+            H = int(W1.shape[0])
+            if hidden is None:
+                hidden = H
+            if H != hidden or tuple(W1.shape) != (H, nw.obs_dims[i]) or tuple(b1.shape) != (H,) or \
+                    tuple(W2.shape) != (5, H) or tuple(b2.shape) != (5,):
+                raise ValueError("policy %d: expected W1 [%d, %d], b1 [%d], W2 [5, %d], b2 [5]"
+                                 % (i, hidden, nw.obs_dims[i], hidden, hidden))
+            parts = (W1.t().contiguous(), b1.contiguous(), W2.contiguous(), b2.contiguous())   # W1 input-major for the kernel
+            keep.append(parts)
+            for lst, t in zip(ptrs, parts):
+                lst.append(t.data_ptr())
+        out = nw.out if self.reuse_buffers else nw.new_outputs()
+        rew_steps = torch.empty((T, self.n, N), dtype=torch.float32, device=nw.device) if per_step_rewards else None
+        actions = [torch.empty((T, N, 5), dtype=torch.float32, device=nw.device) for _ in range(self.n)] if record_actions else None
+        nw.rollout_policy(*[_lib.ptr_array(p) for p in ptrs], hidden, T, out, self._flags(), rew_steps,
+                          _lib.ptr_array([a.data_ptr() for a in actions]) if actions is not None else None)
+        self._last_out = out
+        world._obs_valid = False
+        info_n = {'n': [{} for _ in range(self.n)]}
+        return list(out.obs), list(out.rew_list), list(out.done_list), info_n, {"actions": actions, "rewards": rew_steps}
+
     # ---- user scenarios: native _set_action + World.step, callbacks in the user's torch code -------
     def _step_custom(self, action_n, nw, flags):
         import torch

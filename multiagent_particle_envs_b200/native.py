@@ -261,6 +261,18 @@ class NativeWorld(ShapeHandle):
                                    self._stream()), "mpe_rollout")
         return out
 
+    def rollout_policy(self, w1_ptrs, b1_ptrs, w2_ptrs, b2_ptrs, hidden, n_steps, out=None, flags=0, rew_steps=None,
+                       act_rec_ptrs=None):
+        """n_steps fused steps in ONE launch with every agent's two-layer perceptron evaluated inside the kernel
+        (mpe_rollout_policy); pointer arrays hold one device pointer per agent."""
+        out = out or self.out
+        pv, lm, comm, goal = self._state_ptrs()
+        check(self.lib.mpe_rollout_policy(self.handle, pv, lm, comm, goal, w1_ptrs, b1_ptrs, w2_ptrs, b2_ptrs, int(hidden),
+                                          int(n_steps), out.obs_ptrs, out.rew_ptr,
+                                          rew_steps.data_ptr() if rew_steps is not None else None, act_rec_ptrs,
+                                          out.done_ptr, flags, self._stream()), "mpe_rollout_policy")
+        return out
+
     # ---- host callers (what the reference's callers hold: NumPy arrays) -----------------------
     def host_staging(self):
         if self._host is None:

@@ -246,3 +246,62 @@ def test_open_loop_rollout_equals_repeated_steps(tag, n, T):
     env_c.reset()
     obs_c, rew_c, _, _ = env_c.rollout(seqs)
     assert all(torch.equal(x, y) for x, y in zip(obs_c, obs_r)) and torch.equal(torch.stack(list(rew_c)), rew_sum)
+
+
+@pytest.mark.parametrize("tag,n,T,H", [("simple_spread_n3", 2049, 12, 32), ("simple_spread_n3", 1000, 8, 64),
+                                       ("simple_tag", 1031, 10, 32), ("simple_tag", 512, 5, 64), ("simple", 257, 6, 64)])
+def test_closed_loop_policy_rollout(tag, n, T, H):
+    """env.rollout_policy (mpe_rollout_policy: T steps in one launch, every agent's two-layer actor evaluated inside the
+    kernel from observations that never leave the registers):
+      (1) the actions it records, fed to T ordinary fused steps of a twin env, reproduce the final state, the final
+          observations, every step's rewards and the reward sums BIT FOR BIT (physics / reward / observation parity);
+      (2) every recorded action equals softmax(W2 relu(W1 obs + b1) + b2) evaluated in float64 on the twin's observations
+          to 1e-5 (the fp32 perceptron, FMA accumulation in a fixed order)."""
+    env_a = make_product_env(tag, num_envs=n, seed=9)
+    env_b = make_product_env(tag, num_envs=n, seed=9)
+    env_a.reset()
+    obs_b = env_b.reset()
+    na, nb = env_a.world.native, env_b.world.native
+    assert torch.equal(na.agent_pv, nb.agent_pv)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    policies = []
+    for od in na.obs_dims:
+        policies.append((torch.randn(H, od, device="cuda", generator=g) * 0.7, torch.randn(H, device="cuda", generator=g) * 0.3,
+                         torch.randn(5, H, device="cuda", generator=g) * 0.5, torch.randn(5, device="cuda", generator=g) * 0.2))
+    obs_r, rew_r, done_r, info_r, extras = env_a.rollout_policy(policies, T, record_actions=True, per_step_rewards=True)
+    actions, rew_steps = extras["actions"], extras["rewards"]
+    rew_sum = torch.zeros(env_b.n, n, device="cuda")
+    for t in range(T):
+        for i, (W1, b1, W2, b2) in enumerate(policies):          # (2) the actor, in float64, on the twin's observations
+            o = obs_b[i].double()
+            logits = torch.relu(o @ W1.double().t() + b1.double()) @ W2.double().t() + b2.double()
+            want = torch.softmax(logits, -1)
+            assert torch.allclose(actions[i][t].double(), want, rtol=1e-5, atol=1e-6), (t, i)
+        obs_b, rew_s, done_s, _ = env_b.step([a[t] for a in actions])     # (1) replay the recorded actions
+        rew_sum += torch.stack(list(rew_s))
+        assert torch.equal(rew_steps[t], torch.stack(list(rew_s))), t
+    torch.cuda.synchronize()
+    assert torch.equal(na.agent_pv, nb.agent_pv)
+    for x, y in zip(obs_r, obs_b):
+        assert torch.equal(x, y)
+    assert torch.equal(torch.stack(list(rew_r)), rew_sum)
+    assert not any(bool(d.any()) for d in done_r)
+    # nn.Module policies and no records: same result
+    env_c = make_product_env(tag, num_envs=n, seed=9)
+    env_c.reset()
+    mods = []
+    for W1, b1, W2, b2 in policies:
+        m = torch.nn.Sequential(torch.nn.Linear(W1.shape[1], H), torch.nn.ReLU(), torch.nn.Linear(H, 5)).cuda()
+        with torch.no_grad():
+            m[0].weight.copy_(W1); m[0].bias.copy_(b1); m[2].weight.copy_(W2); m[2].bias.copy_(b2)
+        mods.append(m)
+    obs_c, rew_c, _, _, ex = env_c.rollout_policy(mods, T)
+    assert ex["actions"] is None and all(torch.equal(x, y) for x, y in zip(obs_c, obs_r))
+    assert torch.equal(torch.stack(list(rew_c)), rew_sum)
+    # scenarios without the policy kernel refuse loudly
+    env_w = make_product_env("simple_world_comm", num_envs=64)
+    env_w.reset()
+    from multiagent_particle_envs_b200._lib import MpeError
+    with pytest.raises(MpeError):
+        env_w.rollout_policy([(torch.zeros(32, od, device="cuda"), torch.zeros(32, device="cuda"), torch.zeros(5, 32, device="cuda"),
+                               torch.zeros(5, device="cuda")) for od in env_w.world.native.obs_dims], 2)
