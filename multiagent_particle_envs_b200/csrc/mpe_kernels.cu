@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <type_traits>
 #include <utility>
 
 #include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges cost a few ns unless a profiler is attached
@@ -1218,11 +1219,15 @@ static Program make_program() {
     p.fn[kSetAction] = mpe_kernel<P, kSetAction>;
     p.fn[kWorldStep] = mpe_kernel<P, kWorldStep>;
     p.fn[kObserve] = mpe_kernel<P, kObserve>;
-    if constexpr (P::A >= 2 && pair_count<P>() * 64 <= Shape<P>::kWarpFloats - Shape<P>::obs_base())
+    // the two restructurings that measurements rejected (warp pairs, software-pipelined persistent grid) stay available as
+    // opt-in, bit-identical alternatives for the BASELINE.json worlds only (compile time)
+    constexpr bool kAlternatives = PolicyBuilt<P>::value || std::is_same<P, Spread<6>>::value ||
+                                   std::is_same<P, WorldComm<4, 2, 1, 2>>::value;
+    if constexpr (kAlternatives && P::A >= 2 && pair_count<P>() * 64 <= Shape<P>::kWarpFloats - Shape<P>::obs_base())
         p.split_fn = mpe_kernel<P, kFusedStep, true>;     // (the pair exchange must fit the observation tiles)
     if constexpr (Shape<P>::all_act_dense()) p.hot_fn = mpe_kernel<P, kFusedStep, false, true>;
     if constexpr (Shape<P>::all_act_dense() && P::kLowRegVariant) p.hot_dense_fn = mpe_kernel<P, kFusedStep, false, true, true>;
-    p.pipe_fn = Shape<P>::all_act_dense() ? mpe_pipe_kernel<P> : nullptr;
+    if constexpr (kAlternatives && Shape<P>::all_act_dense()) p.pipe_fn = mpe_pipe_kernel<P>;
     p.pipe_smem = Shape<P>::kPipeWarpBytes;
     p.rollout_fn = mpe_rollout_kernel<P>;
     p.rollout_smem = Shape<P>::kRolloutWarpBytes;
