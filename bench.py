@@ -86,6 +86,14 @@ L2_MULTIPLE = 8     # ring inputs >= 8 x L2.  Measured (profiles/traffic.json): 
 #                     the input lines resident and the replacement is not LRU; 8 x L2 + a read-flush before the region
 
 
+def input_bytes_from_shapes(sh):
+    """bytes a step READS per world (state it looks at + goal indices + actions), from a library shape handle"""
+    from multiagent_particle_envs_b200 import _lib
+    A, L = sh.n_agents, sh.n_landmarks
+    unread = {_lib.SCN_CRYPTO: 4 * A + 2 * L, _lib.SCN_SPEAKER_LISTENER: 4}.get(int(sh.desc.scenario), 0)
+    return 4 * (4 * A + 2 * L + sh.n_goals - unread + sum(sh.act_dims))
+
+
 def ring_size(input_bytes_per_env, n_env, requested=0, cap=MAX_RING, l2_multiple=L2_MULTIPLE):
     need = int(l2_multiple * L2_BYTES / (input_bytes_per_env * n_env)) + 1
     return max(3, min(need, cap), requested or 0)
@@ -419,9 +427,7 @@ class Ring(object):
         self.n_agents = probe.n
         self.bytes_per_env = sh.bytes_per_env_step
         mov = [bool(a.movable) for a in probe.agents]
-        A, L = sh.n_agents, sh.n_landmarks
-        unread = {_lib.SCN_CRYPTO: 4 * A + 2 * L, _lib.SCN_SPEAKER_LISTENER: 4}.get(int(sh.desc.scenario), 0)
-        self.input_bytes_per_env = 4 * (4 * A + 2 * L + sh.n_goals - unread + sum(sh.act_dims))
+        self.input_bytes_per_env = input_bytes_from_shapes(sh)
         self.R = ring_size(self.input_bytes_per_env, n_env, requested_ring, max_ring)
         self.bytes_per_step = self.bytes_per_env * n_env
         self.slots = []

@@ -38,8 +38,8 @@ def main():
     wr = sum(tot["dram__bytes_write.sum"]) / args.launches
     hit = tot.get("lts__t_sector_hit_rate.pct", [0.0])[0]
     ns = tot.get("gpu__time_duration.sum", [0.0])[0] / args.launches
-    w = bench.scenario_world(args.scenario, kw)
-    _, _, bpe, ibpe = bench.shapes_from_oracle(w.descriptor())
+    sh = bench.scenario_world(args.scenario, kw).native_shapes()      # device-less library handle: shapes only
+    bpe, ibpe = sh.bytes_per_env_step, bench.input_bytes_from_shapes(sh)
     R = bench.ring_size(ibpe, args.num_envs, args.ring)
     alg = bpe * args.num_envs
     key = bench.traffic_key(args.scenario, kw, args.num_envs)
