@@ -286,6 +286,7 @@ def test_bench_shape_formula_equals_library(tag):
     act, obs, bpe, ibpe = bench.shapes_from_oracle(w.descriptor())
     sh = w.native_shapes()
     assert act == sh.act_dims and obs == sh.obs_dims and bpe == sh.bytes_per_env_step
+    assert ibpe == bench.input_bytes_from_shapes(sh)        # what the GPU arm sizes its ring on
     R = bench.ring_size(ibpe, 65536)
     assert 0 < ibpe < bpe and (R == bench.MAX_RING or R * ibpe * 65536 > bench.L2_MULTIPLE * bench.L2_BYTES)
     assert bench.ring_size(ibpe, 1 << 26) == 3      # huge batches: the minimum ring
