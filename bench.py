@@ -251,7 +251,7 @@ def _best_process_count(desc, scenario, kw, shared):
     cands = sorted({max(1, cores // 8), max(1, cores // 4), max(1, cores // 2), cores})
     best = (0.0, cores)
     for p in cands:
-        rate, _ = _cpu_throughput(desc, scenario, kw, p, 10, 150, shared)
+        rate, _ = _cpu_throughput(desc, scenario, kw, p, 20, 300, shared)
         if rate > best[0]:
             best = (rate, p)
     return best[1], best[0]
@@ -266,7 +266,10 @@ def cpu_reference_path(desc, scenario, kw, shared, steps, warmup, max_seconds):
     steps = int(max(500, min(steps, max_seconds * per_proc)))
     warmup = int(max(50, min(warmup, 0.25 * max_seconds * per_proc)))
     t0 = time.perf_counter()
-    total, kind = _cpu_throughput(desc, scenario, kw, procs, warmup, steps, shared)
+    total, kind = 0.0, "port"
+    for _ in range(2):      # the better of two timed repetitions: gives the CPU arm its best shot, damps box noise
+        rate, kind = _cpu_throughput(desc, scenario, kw, procs, warmup, steps, shared)
+        total = max(total, rate)
     dt = time.perf_counter() - t0
     cpu_model = ""
     try:
@@ -280,7 +283,7 @@ def cpu_reference_path(desc, scenario, kw, shared, steps, warmup, max_seconds):
             else "oracle/np_port.py (per-world NumPy float64 restatement at the reference's granularity)")
     return {"value": total, "unit": UNIT, "cores": procs, "kind": kind, "cpu_model": cpu_model,
             "sample": "%d processes (best of the probed counts; affinity reports %d CPUs) x %d env.step calls of one %s "
-                      "world each after %d warm-up calls, through %s; softmax actions, reset every 25 steps; %.1f s wall"
+                      "world each after %d warm-up calls (better of two repetitions), through %s; softmax actions, reset every 25 steps; %.1f s wall"
                       % (procs, len(os.sched_getaffinity(0)), steps, scenario, warmup, what, dt),
             "per_process": total / procs, "steps_timed_per_process": steps, "warmup_per_process": warmup, "seconds": dt}
 
