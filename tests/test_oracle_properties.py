@@ -107,3 +107,33 @@ def test_fp32_build_stays_within_north_star_tolerance(seed, tag):
     b = o32.step(pv, lm, comm, act, 0, goal=goal)
     np.testing.assert_allclose(b[0], a[0], rtol=1e-5, atol=1e-6)     # state
     np.testing.assert_allclose(b[2], a[2], rtol=1e-5, atol=1e-6)     # observations
+
+
+def test_flag_mismatch_accounting_bites():
+    """helpers.explain_flag_mismatches (the replacement of the percentage budgets): a reward difference is accepted only
+    if it is a whole number of contact quanta AND some pair of that world sits within 2e-6 of a threshold"""
+    import pytest
+    from helpers import explain_flag_mismatches
+    a_size, l_size = [0.15, 0.15, 0.15], [0.05, 0.05, 0.05]
+    pv = np.zeros((4, 3, 4))
+    pv[:, 0, 0:2] = (-0.8, -0.8)
+    pv[:, 1, 0:2] = (0.8, 0.8)
+    pv[:, 2, 0:2] = (0.8, -0.8)
+    lm = np.full((4, 3, 2), 5.0)                      # far away: no landmark threshold nearby
+    pv[1, 1, 0:2] = (-0.8 + 0.3 + 3e-7, -0.8)         # world 1: agents 0 and 1 a hair outside contact (0.15 + 0.15)
+    ref = np.zeros((4, 3))
+    same = ref.copy()
+    assert explain_flag_mismatches("simple_spread_n3", same, ref, None, None, pv, lm, a_size, l_size) == 0
+    flipped = ref.copy()
+    flipped[1] -= 2.0                                  # fp32 saw the contact: both agents lose 1, shared sum -2: explained
+    assert explain_flag_mismatches("simple_spread_n3", flipped, ref, None, None, pv, lm, a_size, l_size) == 1
+    wrong_world = ref.copy()
+    wrong_world[2] -= 1.0                              # a whole quantum, but no pair of world 2 is near a threshold
+    with pytest.raises(AssertionError):
+        explain_flag_mismatches("simple_spread_n3", wrong_world, ref, None, None, pv, lm, a_size, l_size)
+    not_quantum = ref.copy()
+    not_quantum[1] -= 0.37                             # near a threshold, but not a multiple of the contact quantum
+    with pytest.raises(AssertionError):
+        explain_flag_mismatches("simple_spread_n3", not_quantum, ref, None, None, pv, lm, a_size, l_size)
+    with pytest.raises(AssertionError):                # scenarios without indicator terms tolerate nothing
+        explain_flag_mismatches("simple_push", flipped, ref, None, None, pv, lm, a_size, l_size)
